@@ -1,0 +1,425 @@
+// tcgen05 tensor-core GEMM for sm_100a:  D[M,N] = act([A0|A1][M,K] * W[N,K]^T + bias) (+ residual)
+// bf16 operands, fp32 accumulation in TMEM, bf16 output.
+//
+// This kernel carries every 1x1-conv / linear layer of the denoiser in throughput mode (reference:
+// F.conv1d / nn.Linear calls of scene_synthesis/networks/denoise_net.py:91,183,214-217,244-245,487-502).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A (128 x 64) and W (BN x 64)
+//               into a STAGES-deep shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block,
+//               accumulating into one of two TMEM buffers; tcgen05.commit releases smem slots / signals
+//               the epilogue
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> bf16 -> HBM;
+//               double-buffered TMEM lets the epilogue of tile i overlap the MMAs of tile i+1
+// Both operands are K-major (activations [rows, K], weights [N, K] exactly as PyTorch stores them), so no
+// transposes exist anywhere in the data path.  A "virtual concat" [A0|A1] (the U-Net skip connections,
+// denoise_net.py:562,566,573) is served by switching tensor maps inside the k loop.
+#include <cuda.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "kernels.cuh"
+
+namespace ds {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int TC_THREADS = 192;
+static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+static constexpr uint64_t WAIT_TIMEOUT_CYCLES = 4000000000ull;   // ~2 s: a protocol bug traps instead of hanging
+
+struct TcEpi {
+  const float* bias;
+  bf16* d; int ldd;
+  const bf16* res; int ldres;
+  int act;
+  int M, N;
+  int kb0, kb1;          // k-blocks taken from A0 and from A1
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a mis-programmed pipeline traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+      if (err_flag) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// D(tmem, fp32) (+)= A(smem, bf16) * B(smem, bf16)^T, M = 128, N from the instruction descriptor, K = 16
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers (256 or 512 columns)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+                                    (uint32_t(BM >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+          const __grid_constant__ CUtensorMap tm_w, TcEpi epi, int* err_flag) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a0);
+    tma_prefetch_desc(&tm_a1);
+    tma_prefetch_desc(&tm_w);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_m = (epi.M + BM - 1) / BM;
+  const int num_n = epi.N / BN;
+  const int total = num_m * num_n;
+  const int kblocks = epi.kb0 + epi.kb1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m_idx = tile % num_m, n_idx = tile / num_m;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          if (kb < epi.kb0) tma_load_2d(sa, &tm_a0, kb * BK, m_idx * BM, full_bar(stage));
+          else tma_load_2d(sa, &tm_a1, (kb - epi.kb0) * BK, m_idx * BM, full_bar(stage));
+          tma_load_2d(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN, full_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int ab = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(ab * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));          // smem slot reusable once these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(ab));               // accumulator complete -> epilogue
+        if (++ab == 2) { ab = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int ab = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int m_idx = tile % num_m, n_idx = tile / num_m;
+      const int m = m_idx * BM + row_in_tile;
+      mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + uint32_t(c * 32), r);
+        if (m < epi.M) {
+          const int n0 = n_idx * BN + c * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (epi.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(epi.bias + n0 + j);
+          }
+          if (epi.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (epi.act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+          }
+          if (epi.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(epi.res + (int64_t)m * epi.ldres + n0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk = __ldg(rp + g);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __bfloat1622float2(h2[e]);
+                v[g * 8 + e * 2] += f.x;
+                v[g * 8 + e * 2 + 1] += f.y;
+              }
+            }
+          }
+          uint4* dp = reinterpret_cast<uint4*>(epi.d + (int64_t)m * epi.ldd + n0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
+            dp[g] = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(ab));
+      if (++ab == 2) { ab = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+struct TcGemmPlan {
+  CUtensorMap tm_a0, tm_a1, tm_w;
+  TcEpi epi;
+  int bn;
+  int num_sms;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static int g_num_sms = 0;
+static int* g_err_flag = nullptr;       // pinned host memory, device-visible
+
+bool tc_runtime_available(char* err, int err_len) {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    if (err) snprintf(err, err_len, "cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+    return false;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10) {
+    if (err) snprintf(err, err_len, "tcgen05 GEMM needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
+    return false;
+  }
+  g_num_sms = prop.multiProcessorCount;
+  if (!g_err_flag) {
+    cudaHostAlloc((void**)&g_err_flag, sizeof(int), cudaHostAllocMapped);
+    *g_err_flag = 0;
+  }
+  cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+  g_encode = (PFN_encodeTiled)fn;
+  return true;
+}
+
+static bool encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
+                      uint32_t box_rows, char* err, int err_len) {
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) snprintf(err, err_len, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu pitch=%llu box=%u",
+                      (int)r, (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)pitch_elems,
+                      box_rows);
+    return false;
+  }
+  return true;
+}
+
+TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int err_len) {
+  if (!tc_runtime_available(err, err_len)) return nullptr;
+  const int K = g.k0 + g.k1;
+  if (g.k0 % BK || g.k1 % BK || g.N % 128 || K == 0) {
+    if (err) snprintf(err, err_len, "tcgen05 GEMM needs K%%64==0 and N%%128==0 (k0=%d k1=%d N=%d)", g.k0, g.k1, g.N);
+    return nullptr;
+  }
+  if ((g.lda0 % 8) || (g.a1 && (g.lda1 % 8)) || (g.ldw % 8) || (g.ldd % 8) || (g.res && (g.ldres % 8)) ||
+      ((uintptr_t)g.a0 % 16) || ((uintptr_t)g.w % 16) || ((uintptr_t)g.d % 16) || (g.a1 && ((uintptr_t)g.a1 % 16)) ||
+      (g.res && ((uintptr_t)g.res % 16))) {
+    if (err) snprintf(err, err_len, "tcgen05 GEMM needs 16-byte aligned operands and pitches");
+    return nullptr;
+  }
+  TcGemmPlan* p = new TcGemmPlan();
+  memset(p, 0, sizeof(*p));
+  // BN = 256 halves the A re-reads; keep 128 when N is not a multiple of 256
+  p->bn = (g.N % 256 == 0) ? 256 : 128;
+  p->num_sms = g_num_sms;
+  bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, BM, err, err_len);
+  if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, BM, err, err_len);
+  if (ok && !g.a1) p->tm_a1 = p->tm_a0;
+  if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, p->bn, err, err_len);
+  if (!ok) {
+    delete p;
+    return nullptr;
+  }
+  p->epi.bias = g.bias;
+  p->epi.d = (bf16*)g.d;
+  p->epi.ldd = g.ldd;
+  p->epi.res = (const bf16*)g.res;
+  p->epi.ldres = g.ldres;
+  p->epi.act = g.act;
+  p->epi.M = g.M;
+  p->epi.N = g.N;
+  p->epi.kb0 = g.k0 / BK;
+  p->epi.kb1 = g.k1 / BK;
+  return p;
+}
+void tc_plan_destroy(TcGemmPlan* p) { delete p; }
+
+int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
+  TcEpi epi = p->epi;
+  epi.M = M;
+  const int num_m = (M + BM - 1) / BM;
+  const int total = num_m * (epi.N / p->bn);
+  if (total == 0) return 0;
+  const int grid = total < p->num_sms ? total : p->num_sms;
+  int* flag_dev = nullptr;
+  cudaHostGetDevicePointer((void**)&flag_dev, g_err_flag, 0);
+  if (p->bn == 256)
+    k_gemm_tc<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+  else
+    k_gemm_tc<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+  return (int)cudaPeekAtLastError();
+}
+
+int tc_error_flag() { return g_err_flag ? *g_err_flag : 0; }
+
+}  // namespace ds

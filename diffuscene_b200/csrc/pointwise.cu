@@ -1,0 +1,756 @@
+// Non-GEMM kernels of the denoiser and of the diffusion step (sm_100a).
+//
+// Activation matrices are token-major: row r = scene (r / n_obj), object (r % n_obj); columns are
+// channels.  One warp owns one (scene, group) for GroupNorm, one token for LayerNorm and one
+// (scene, head) for the attention cores, so every reduction is a register / shuffle reduction.
+// Reference semantics: scene_synthesis/networks/denoise_net.py (Block :160-176, LayerNorm :93-102,
+// LinearAttention :208-235, Attention :237-259, LinearAttentionCross :261-297) and
+// scene_synthesis/networks/diffusion_ddpm.py (q_sample :276-286, p_sample :339-352, p_losses :520-652).
+#include "kernels.cuh"
+
+namespace ds {
+
+static inline int cdiv(int64_t a, int64_t b) { return int((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// input pack / output unpack
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pack_input(const float* __restrict__ x, T* __restrict__ out, int ld_out, int M, int d) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * ld_out) return;
+  int r = int(i / ld_out), c = int(i % ld_out);
+  stf(out + i, c < d ? x[(int64_t)r * d + c] : 0.0f);
+}
+template <typename T>
+void launch_pack_input(const float* x, T* out, int ld_out, int M, int d, cudaStream_t s) {
+  int64_t n = (int64_t)M * ld_out;
+  k_pack_input<T><<<cdiv(n, 256), 256, 0, s>>>(x, out, ld_out, M, d);
+}
+
+template <typename T>
+__global__ void k_unpack_output(const T* __restrict__ in, int ld_in, float* __restrict__ out, int M, int d) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * d) return;
+  int r = int(i / d), c = int(i % d);
+  out[i] = ldf(in + (int64_t)r * ld_in + c);
+}
+template <typename T>
+void launch_unpack_output(const T* in, int ld_in, float* out, int M, int d, cudaStream_t s) {
+  int64_t n = (int64_t)M * d;
+  k_unpack_output<T><<<cdiv(n, 256), 256, 0, s>>>(in, ld_in, out, M, d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm (+ affine) (+ FiLM) + SiLU (+ residual)      one warp per (scene, group)
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(128) k_groupnorm(const T* __restrict__ in, int ld_in, T* __restrict__ out,
+                                                   int ld_out, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, FilmRef film,
+                                                   const T* __restrict__ res, int ld_res, int n_scenes, int n_obj,
+                                                   int C, int groups) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= n_scenes * groups) return;
+  const int scene = w / groups, grp = w % groups;
+  const int cpg = C / groups;
+  const int64_t row0 = (int64_t)scene * n_obj;
+  const int c0 = grp * cpg;
+  const float inv_cnt = 1.0f / float(n_obj * cpg);
+
+  float s = 0.f;
+  for (int r = 0; r < n_obj; ++r)
+    for (int c = lane; c < cpg; c += 32) s += ldf(in + (row0 + r) * ld_in + c0 + c);
+  const float mean = warp_sum(s) * inv_cnt;
+  float q = 0.f;
+  for (int r = 0; r < n_obj; ++r)
+    for (int c = lane; c < cpg; c += 32) {
+      float v = ldf(in + (row0 + r) * ld_in + c0 + c) - mean;
+      q += v * v;
+    }
+  const float var = warp_sum(q) * inv_cnt;
+  const float rstd = EXACT ? 1.0f / sqrtf(var + 1e-5f) : rsqrtf(var + 1e-5f);
+
+  for (int r = 0; r < n_obj; ++r) {
+    const float* frow = nullptr;
+    if (film.mode == FILM_TIME) frow = film.base + (int64_t)film.t[scene] * film.row_stride;
+    else if (film.mode == FILM_OBJECT) frow = film.base + (int64_t)r * film.row_stride;
+    else if (film.mode == FILM_TOKEN) frow = film.base + (row0 + r) * film.row_stride;
+    for (int c = lane; c < cpg; c += 32) {
+      const int ch = c0 + c;
+      float v = (ldf(in + (row0 + r) * ld_in + ch) - mean) * rstd * gamma[ch] + beta[ch];
+      if (frow) v = v * (frow[ch] + 1.0f) + frow[C + ch];
+      v = EXACT ? silu_exact(v) : silu(v);
+      if (res) v += ldf(res + (row0 + r) * ld_res + ch);
+      stf(out + (row0 + r) * ld_out + ch, v);
+    }
+  }
+}
+template <typename T>
+void launch_groupnorm(const T* in, int ld_in, T* out, int ld_out, const float* gamma, const float* beta,
+                      FilmRef film, const T* res, int ld_res, int n_scenes, int n_obj, int C, int groups,
+                      cudaStream_t s) {
+  int warps = n_scenes * groups;
+  constexpr bool EX = sizeof(T) == 4;
+  k_groupnorm<T, EX><<<cdiv(warps, 4), 128, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, film, res, ld_res,
+                                                    n_scenes, n_obj, C, groups);
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel LayerNorm (no bias) (+ residual)                one warp per token, C <= 1024
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(128) k_layernorm(const T* __restrict__ in, int ld_in, T* __restrict__ out,
+                                                   int ld_out, const float* __restrict__ g,
+                                                   const T* __restrict__ res, int ld_res, int M, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float v[32];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    int c = i * 32 + lane;
+    v[i] = c < C ? ldf(in + row * ld_in + c) : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / float(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    int c = i * 32 + lane;
+    float dlt = c < C ? v[i] - mean : 0.f;
+    q += dlt * dlt;
+  }
+  const float var = warp_sum(q) / float(C);
+  const float rstd = EXACT ? 1.0f / sqrtf(var + 1e-5f) : rsqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    int c = i * 32 + lane;
+    if (c < C) {
+      float y = (v[i] - mean) * rstd * g[c];
+      if (res) y += ldf(res + row * ld_res + c);
+      stf(out + row * ld_out + c, y);
+    }
+  }
+}
+template <typename T>
+void launch_layernorm(const T* in, int ld_in, T* out, int ld_out, const float* g, const T* res, int ld_res, int M,
+                      int C, cudaStream_t s) {
+  constexpr bool EX = sizeof(T) == 4;
+  k_layernorm<T, EX><<<cdiv(M, 4), 128, 0, s>>>(in, ld_in, out, ld_out, g, res, ld_res, M, C);
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention cores: 4 heads x 32 channels, one warp per (scene, head), lane = head channel
+// dynamic smem: 4 warps x 3 x n_obj x 33 floats
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_linattn(const T* __restrict__ qkv, int ld, T* __restrict__ out, int ld_out,
+                                                 int n_scenes, int n) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int scene = blockIdx.x;
+  float* qs = sm + h * 3 * n * 32;
+  float* ks = qs + n * 32;
+  float* vs = ks + n * 32;
+  const int64_t row0 = (int64_t)scene * n;
+  const float scale = 0.17677669529663687f;   // 32^-0.5
+  // q: softmax over the 32 head channels of each token, then * scale (denoise_net.py:226-229)
+  float kmax = -INFINITY;
+  for (int r = 0; r < n; ++r) {
+    const T* p = qkv + (row0 + r) * ld + h * 32 + lane;
+    float q = ldf(p), k = ldf(p + 128), v = ldf(p + 256);
+    float m = warp_max(q);
+    float e = expf(q - m);
+    float ssum = warp_sum(e);
+    qs[r * 32 + lane] = e / ssum * scale;
+    ks[r * 32 + lane] = k;
+    vs[r * 32 + lane] = v;
+    kmax = fmaxf(kmax, k);
+  }
+  // k: softmax over tokens for each channel (lane-private column)
+  float ksum = 0.f;
+  for (int r = 0; r < n; ++r) {
+    float e = expf(ks[r * 32 + lane] - kmax);
+    ks[r * 32 + lane] = e;
+    ksum += e;
+  }
+  const float kinv = 1.0f / ksum;
+  for (int r = 0; r < n; ++r) ks[r * 32 + lane] *= kinv;
+  __syncwarp();
+  // ctx[d][e] = sum_n k[d,n] v[e,n]; this lane keeps column e = lane
+  float ctx[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) ctx[d] = 0.f;
+  for (int r = 0; r < n; ++r) {
+    float v = vs[r * 32 + lane];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) ctx[d] += ks[r * 32 + d] * v;
+  }
+  // out[e,n] = sum_d ctx[d][e] q[d,n]
+  for (int r = 0; r < n; ++r) {
+    float o = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o += ctx[d] * qs[r * 32 + d];
+    stf(out + (row0 + r) * ld_out + h * 32 + lane, o);
+  }
+}
+template <typename T>
+void launch_linattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int n_obj, cudaStream_t s) {
+  size_t smem = size_t(4) * 3 * n_obj * 32 * sizeof(float);
+  k_linattn<T><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_softattn(const T* __restrict__ qkv, int ld, T* __restrict__ out, int ld_out,
+                                                  int n_scenes, int n) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int scene = blockIdx.x;
+  float* qs = sm + h * 3 * n * 33;
+  float* ks = qs + n * 33;
+  float* vs = ks + n * 33;
+  const int64_t row0 = (int64_t)scene * n;
+  const float scale = 0.17677669529663687f;
+  for (int r = 0; r < n; ++r) {
+    const T* p = qkv + (row0 + r) * ld + h * 32 + lane;
+    qs[r * 33 + lane] = ldf(p) * scale;
+    ks[r * 33 + lane] = ldf(p + 128);
+    vs[r * 33 + lane] = ldf(p + 256);
+  }
+  __syncwarp();
+  for (int i = 0; i < n; ++i) {
+    // this lane scores keys j = lane and lane + 32 (n <= 64)
+    float s0 = -INFINITY, s1 = -INFINITY;
+    if (lane < n) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) a += qs[i * 33 + d] * ks[lane * 33 + d];
+      s0 = a;
+    }
+    if (lane + 32 < n) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) a += qs[i * 33 + d] * ks[(lane + 32) * 33 + d];
+      s1 = a;
+    }
+    float m = warp_max(fmaxf(s0, s1));
+    float e0 = lane < n ? expf(s0 - m) : 0.f;
+    float e1 = lane + 32 < n ? expf(s1 - m) : 0.f;
+    float inv = 1.0f / warp_sum(e0 + e1);
+    e0 *= inv;
+    e1 *= inv;
+    float o = 0.f;
+    for (int j = 0; j < n; ++j) {
+      float p = j < 32 ? __shfl_sync(0xffffffffu, e0, j) : __shfl_sync(0xffffffffu, e1, j - 32);
+      o += p * vs[j * 33 + lane];
+    }
+    stf(out + (row0 + i) * ld_out + h * 32 + lane, o);
+  }
+}
+template <typename T>
+void launch_softattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int n_obj, cudaStream_t s) {
+  size_t smem = size_t(4) * 3 * n_obj * 33 * sizeof(float);
+  k_softattn<T><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+}
+
+// cross linear attention -- text side, once per sampling call: ctx[scene][h][d][e] (fp32)
+__global__ void __launch_bounds__(128) k_xattn_prepare(const float* __restrict__ kv, int ld_kv,
+                                                       float* __restrict__ ctx, int n_scenes, int L) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int scene = blockIdx.x;
+  float* ks = sm + h * 2 * L * 32;
+  float* vs = ks + L * 32;
+  const int64_t row0 = (int64_t)scene * L;
+  float kmax = -INFINITY;
+  for (int l = 0; l < L; ++l) {
+    const float* p = kv + (row0 + l) * ld_kv + h * 32 + lane;
+    float k = p[0];
+    ks[l * 32 + lane] = k;
+    vs[l * 32 + lane] = p[128];
+    kmax = fmaxf(kmax, k);
+  }
+  float ksum = 0.f;
+  for (int l = 0; l < L; ++l) {
+    float e = expf(ks[l * 32 + lane] - kmax);
+    ks[l * 32 + lane] = e;
+    ksum += e;
+  }
+  const float kinv = 1.0f / ksum;
+  for (int l = 0; l < L; ++l) ks[l * 32 + lane] *= kinv;
+  __syncwarp();
+  float acc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    float v = vs[l * 32 + lane];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] += ks[l * 32 + d] * v;
+  }
+  float* o = ctx + ((int64_t)scene * 4 + h) * 1024;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) o[d * 32 + lane] = acc[d];
+}
+void launch_xattn_prepare(const float* kv, int ld_kv, float* ctx, int n_scenes, int L, cudaStream_t s) {
+  size_t smem = size_t(4) * 2 * L * 32 * sizeof(float);
+  k_xattn_prepare<<<n_scenes, 128, smem, s>>>(kv, ld_kv, ctx, n_scenes, L);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_xattn_apply(const T* __restrict__ q, int ldq, const float* __restrict__ ctx,
+                                                     T* __restrict__ out, int ld_out, int n_scenes, int n) {
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int scene = blockIdx.x;
+  const float* cx = ctx + ((int64_t)scene * 4 + h) * 1024;
+  float c[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) c[d] = cx[d * 32 + lane];
+  const int64_t row0 = (int64_t)scene * n;
+  const float scale = 0.17677669529663687f;
+  for (int r = 0; r < n; ++r) {
+    float qv = ldf(q + (row0 + r) * ldq + h * 32 + lane);
+    float m = warp_max(qv);
+    float e = expf(qv - m);
+    float sm_ = warp_sum(e);
+    float qn = e / sm_ * scale;
+    float o = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o += c[d] * __shfl_sync(0xffffffffu, qn, d);
+    stf(out + (row0 + r) * ld_out + h * 32 + lane, o);
+  }
+}
+template <typename T>
+void launch_xattn_apply(const T* q, int ldq, const float* ctx, T* out, int ld_out, int n_scenes, int n_obj,
+                        cudaStream_t s) {
+  k_xattn_apply<T><<<n_scenes, 128, 0, s>>>(q, ldq, ctx, out, ld_out, n_scenes, n_obj);
+}
+
+// ------------------------------------------------------------------------------------------------
+// time embedding helpers
+// ------------------------------------------------------------------------------------------------
+// out[t][k] = sin(t * f_k), out[t][half + k] = cos(t * f_k); f_k supplied by the host (denoise_net.py:132-139)
+__global__ void k_sinusoid(float* __restrict__ out, const float* __restrict__ freq, int T, int dim) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int half = dim / 2;
+  if (i >= T * half) return;
+  int t = i / half, k = i % half;
+  float a = float(t) * freq[k];
+  out[(int64_t)t * dim + k] = sinf(a);
+  out[(int64_t)t * dim + half + k] = cosf(a);
+}
+static float* g_freq = nullptr;
+static int g_freq_dim = 0;
+void launch_sinusoid(float* out, int T, int dim, cudaStream_t s) {
+  int half = dim / 2;
+  if (g_freq_dim != dim) {
+    if (g_freq) cudaFree(g_freq);
+    cudaMalloc(&g_freq, half * sizeof(float));
+    float* hf = new float[half];
+    const float neg_emb = -float(9.210340371976184 / double(half - 1));   // -(ln 1e4)/(half-1) as fp32
+    for (int k = 0; k < half; ++k) hf[k] = expf(float(k) * neg_emb);
+    cudaMemcpy(g_freq, hf, half * sizeof(float), cudaMemcpyHostToDevice);
+    delete[] hf;
+    g_freq_dim = dim;
+  }
+  k_sinusoid<<<cdiv((int64_t)T * half, 256), 256, 0, s>>>(out, g_freq, T, dim);
+}
+
+__global__ void k_silu_f32(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = silu_exact(in[i]);
+}
+void launch_silu_f32(const float* in, float* out, int64_t n, cudaStream_t s) {
+  k_silu_f32<<<cdiv(n, 256), 256, 0, s>>>(in, out, n);
+}
+
+__global__ void k_t_convert(const int64_t* __restrict__ t, int* __restrict__ out, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) out[i] = int(t[i]);
+}
+void launch_t_convert(const int64_t* t, int* out, int B, cudaStream_t s) {
+  k_t_convert<<<cdiv(B, 256), 256, 0, s>>>(t, out, B);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling-step kernels
+// ------------------------------------------------------------------------------------------------
+// N(0,1) for element quad `qd` of global scene `gs`; independent of how scenes are sharded over GPUs
+__device__ __forceinline__ float4 randn4(uint64_t seed, uint64_t gs, uint32_t qd, uint32_t step, uint32_t stream_id) {
+  uint4 ctr = make_uint4(qd, uint32_t(gs), uint32_t(gs >> 32), step | (stream_id << 24));
+  uint4 r = philox4x32_10(ctr, make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+  float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void k_begin_step(const StepCoef* __restrict__ coef, const StepState* __restrict__ st,
+                             int* __restrict__ t_dev, float* __restrict__ x, const float* __restrict__ partial,
+                             const float* __restrict__ partial_noise, int B, int n_obj, int d, int P, uint64_t seed,
+                             uint64_t scene_offset) {
+  const int step = st->step;
+  const StepCoef c = coef[step];
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < B) t_dev[i] = c.t;
+  if (P > 0) {
+    const int per_part = P * d, quads = (per_part + 3) / 4;
+    if (i < (int64_t)B * quads) {
+      int b = int(i / quads), qd = int(i % quads);
+      float z[4];
+      if (partial_noise) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int e = qd * 4 + k;
+          z[k] = e < per_part ? partial_noise[((int64_t)step * B + b) * per_part + e] : 0.f;
+        }
+      } else {
+        float4 r = randn4(seed, scene_offset + b, qd, step, 1u);
+        z[0] = r.x; z[1] = r.y; z[2] = r.z; z[3] = r.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int e = qd * 4 + k;
+        if (e < per_part)
+          x[(int64_t)b * n_obj * d + e] =
+              __fadd_rn(__fmul_rn(c.q_a, partial[(int64_t)b * per_part + e]), __fmul_rn(c.q_b, z[k]));
+      }
+    }
+  }
+}
+void launch_begin_step(const StepCoef* coef, const StepState* st, int* t_dev, float* x, const float* partial,
+                       const float* partial_noise, int B, int n_obj, int d, int P, uint64_t seed,
+                       uint64_t scene_offset, cudaStream_t s) {
+  int64_t n = B;
+  if (P > 0) {
+    int64_t m = (int64_t)B * ((P * d + 3) / 4);
+    if (m > n) n = m;
+  }
+  k_begin_step<<<cdiv(n, 256), 256, 0, s>>>(coef, st, t_dev, x, partial, partial_noise, B, n_obj, d, P, seed,
+                                            scene_offset);
+}
+
+// x0 = a_x*x + a_o*out ; clamp ; x' = c_0*x0 + c_x*x + c_z*z   (rounding order of diffusion_ddpm.py:236-240,
+// 294-297, 348-350: every product and sum rounded separately, no FMA contraction)
+__device__ unsigned int g_step_done_blocks = 0;
+template <typename T>
+__global__ void k_step_update(const StepCoef* __restrict__ coef, StepState* st, float* __restrict__ x,
+                              const T* __restrict__ model_out, int ld_out, const float* __restrict__ noise, int B,
+                              int n_obj, int d, int clip, uint64_t seed, uint64_t scene_offset) {
+  const int step = st->step;
+  const StepCoef c = coef[step];
+  const int per_scene = n_obj * d, quads = (per_scene + 3) / 4;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < (int64_t)B * quads) {
+    int b = int(i / quads), qd = int(i % quads);
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c.c_z != 0.f) {
+      if (noise) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int e = qd * 4 + k;
+          if (e < per_scene) z[k] = noise[((int64_t)step * B + b) * per_scene + e];
+        }
+      } else {
+        float4 r = randn4(seed, scene_offset + b, qd, step, 0u);
+        z[0] = r.x; z[1] = r.y; z[2] = r.z; z[3] = r.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int e = qd * 4 + k;
+      if (e < per_scene) {
+        int o = e / d, ch = e % d;
+        int64_t xi = (int64_t)b * per_scene + e;
+        float xv = x[xi];
+        float ov = ldf(model_out + ((int64_t)b * n_obj + o) * ld_out + ch);
+        float x0 = __fadd_rn(__fmul_rn(c.a_x, xv), __fmul_rn(c.a_o, ov));
+        if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        float mean = __fadd_rn(__fmul_rn(c.c_0, x0), __fmul_rn(c.c_x, xv));
+        x[xi] = __fadd_rn(mean, __fmul_rn(c.c_z, z[k]));
+      }
+    }
+  }
+  // the last block to finish advances the loop counter (every block has read st->step by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int done = atomicAdd(&g_step_done_blocks, 1u);
+    if (done == gridDim.x - 1) {
+      g_step_done_blocks = 0;
+      st->step = step + 1;
+      __threadfence();
+    }
+  }
+}
+template <typename T>
+void launch_step_update(const StepCoef* coef, StepState* st, float* x, const T* model_out, int ld_out,
+                        const float* noise, int B, int n_obj, int d, int clip, uint64_t seed, uint64_t scene_offset,
+                        cudaStream_t s) {
+  int64_t n = (int64_t)B * ((n_obj * d + 3) / 4);
+  k_step_update<T><<<cdiv(n, 256), 256, 0, s>>>(coef, st, x, model_out, ld_out, noise, B, n_obj, d, clip, seed,
+                                                scene_offset);
+}
+
+__global__ void k_randn(float* __restrict__ out, int B, int per_scene, uint64_t seed, uint64_t scene_offset,
+                        uint32_t stream_id) {
+  const int quads = (per_scene + 3) / 4;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * quads) return;
+  int b = int(i / quads), qd = int(i % quads);
+  float4 r = randn4(seed, scene_offset + b, qd, 0xFFFFFFu, stream_id);
+  float z[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int e = qd * 4 + k;
+    if (e < per_scene) out[(int64_t)b * per_scene + e] = z[k];
+  }
+}
+void launch_randn(float* out, int B, int per_scene, uint64_t seed, uint64_t scene_offset, uint32_t stream_id,
+                  cudaStream_t s) {
+  int64_t n = (int64_t)B * ((per_scene + 3) / 4);
+  k_randn<<<cdiv(n, 256), 256, 0, s>>>(out, B, per_scene, seed, scene_offset, stream_id);
+}
+
+template <typename T>
+__global__ void k_p_sample(const float* __restrict__ x, const T* __restrict__ model_out, int ld_out,
+                           const int* __restrict__ t, const float* __restrict__ noise, float* __restrict__ out,
+                           const float* __restrict__ a_x, const float* __restrict__ a_o,
+                           const float* __restrict__ c1, const float* __restrict__ c2,
+                           const float* __restrict__ sigma, int B, int n_obj, int d, int clip) {
+  const int per_scene = n_obj * d;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * per_scene) return;
+  int b = int(i / per_scene), e = int(i % per_scene);
+  int o = e / d, ch = e % d;
+  int tt = t[b];
+  float xv = x[i];
+  float ov = ldf(model_out + ((int64_t)b * n_obj + o) * ld_out + ch);
+  float x0 = __fadd_rn(__fmul_rn(a_x[tt], xv), __fmul_rn(a_o[tt], ov));
+  if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  float mean = __fadd_rn(__fmul_rn(c1[tt], x0), __fmul_rn(c2[tt], xv));
+  out[i] = __fadd_rn(mean, __fmul_rn(sigma[tt], noise[i]));
+}
+template <typename T>
+void launch_p_sample(const float* x, const T* model_out, int ld_out, const int* t, const float* noise, float* out,
+                     const float* a_x, const float* a_o, const float* c1, const float* c2, const float* sigma, int B,
+                     int n_obj, int d, int clip, cudaStream_t s) {
+  int64_t n = (int64_t)B * n_obj * d;
+  k_p_sample<T><<<cdiv(n, 256), 256, 0, s>>>(x, model_out, ld_out, t, noise, out, a_x, a_o, c1, c2, sigma, B, n_obj,
+                                             d, clip);
+}
+
+__global__ void k_q_sample(const float* __restrict__ x0, const int64_t* __restrict__ t,
+                           const float* __restrict__ noise, float* __restrict__ out,
+                           const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac, int B,
+                           int per_scene) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * per_scene) return;
+  int tt = int(t[i / per_scene]);
+  out[i] = __fadd_rn(__fmul_rn(sqrt_ac[tt], x0[i]), __fmul_rn(sqrt_1mac[tt], noise[i]));
+}
+void launch_q_sample(const float* x0, const int64_t* t, const float* noise, float* out, const float* sqrt_ac,
+                     const float* sqrt_1mac, int B, int per_scene, cudaStream_t s) {
+  int64_t n = (int64_t)B * per_scene;
+  k_q_sample<<<cdiv(n, 256), 256, 0, s>>>(x0, t, noise, out, sqrt_ac, sqrt_1mac, B, per_scene);
+}
+
+// ------------------------------------------------------------------------------------------------
+// p_losses value: one CTA (128 threads) per scene
+// parts[b] = {bbox, trans, size, angle, class, object, objfeat, liou, bbox_iou}
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_p_losses(const float* __restrict__ x0, const float* __restrict__ noise,
+                                                  const float* __restrict__ x_t, const T* __restrict__ model_out,
+                                                  int ld_out, const int64_t* __restrict__ t,
+                                                  const float* __restrict__ sqrt_ac,
+                                                  const float* __restrict__ sqrt_1mac,
+                                                  const float* __restrict__ sqrt_recip_ac,
+                                                  const float* __restrict__ sqrt_recipm1_ac,
+                                                  const float* __restrict__ loss_weight,
+                                                  const float* __restrict__ alphas_cumprod, LossArgs a,
+                                                  float* __restrict__ losses, float* __restrict__ parts) {
+  __shared__ float acc[8];          // trans, size, angle, class, object, objfeat, full, (unused)
+  __shared__ float box[64][6];      // clamped, descaled corners
+  __shared__ float valid[64];
+  __shared__ float iou_acc[3];      // sum(iou*mask), sum(mask), unused
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int tt = int(t[b]);
+  const int n = a.n_obj, d = a.d;
+  if (tid < 8) acc[tid] = 0.f;
+  if (tid < 3) iou_acc[tid] = 0.f;
+  __syncthreads();
+  const float sa = sqrt_ac[tt], sb = sqrt_1mac[tt];
+  const int bb = a.trans + a.size + a.angle;
+  const int c_end = bb + a.cls;
+  const int obj_lo = a.objn > 0 ? c_end : c_end - 1, obj_hi = a.objn > 0 ? c_end + a.objn : c_end;
+  float l[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int e = tid; e < n * d; e += 128) {
+    int o = e / d, ch = e % d;
+    int64_t gi = (int64_t)b * n * d + e;
+    float x0v = x0[gi], nz = noise[gi];
+    float target;
+    if (a.mean_type == 0) target = nz;
+    else if (a.mean_type == 1) target = x0v;
+    else target = __fadd_rn(__fmul_rn(sa, nz), -__fmul_rn(sb, x0v));
+    float ov = ldf(model_out + ((int64_t)b * n + o) * ld_out + ch);
+    float df = target - ov;
+    float se = df * df;
+    l[6] += se;
+    if (a.arrange) {
+      if (ch < a.trans) l[0] += se; else l[2] += se;
+    } else {
+      if (ch < a.trans) l[0] += se;
+      else if (ch < a.trans + a.size) l[1] += se;
+      else if (ch < bb) l[2] += se;
+      else if (ch < c_end) l[3] += se;
+      if (ch >= obj_lo && ch < obj_hi) l[4] += se;
+      if (ch >= c_end + a.objn) l[5] += se;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    float v = warp_sum(l[k]);
+    if ((tid & 31) == 0) atomicAdd(&acc[k], v);
+  }
+  // IoU regulariser (diffusion_ddpm.py:600-635, loss.py:7-102)
+  if (a.loss_iou && !a.arrange) {
+    for (int o = tid; o < n; o += 128) {
+      float rec[7];
+      int chs[7] = {0, 1, 2, a.trans, a.trans + 1, a.trans + 2, a.objn > 0 ? c_end : c_end - 1};
+      for (int k = 0; k < 7; ++k) {
+        int64_t gi = ((int64_t)b * n + o) * d + chs[k];
+        float xt = x_t[gi];
+        float ov = ldf(model_out + ((int64_t)b * n + o) * ld_out + chs[k]);
+        float r;
+        if (a.mean_type == 0) r = __fadd_rn(__fmul_rn(sqrt_recip_ac[tt], xt), -__fmul_rn(sqrt_recipm1_ac[tt], ov));
+        else if (a.mean_type == 1) r = ov;
+        else r = __fadd_rn(__fmul_rn(sa, xt), -__fmul_rn(sb, ov));
+        rec[k] = fminf(fmaxf(r, -1.0f), 1.0f);
+      }
+      valid[o] = a.objn > 0 ? (rec[6] >= 0.f ? 1.f : 0.f) : (rec[6] <= 0.f ? 1.f : 0.f);
+      for (int k = 0; k < 3; ++k) {
+        float tr = (rec[k] + 1.0f) / 2.0f * (a.bounds[3 + k] - a.bounds[k]) + a.bounds[k];
+        float sz = (rec[3 + k] + 1.0f) / 2.0f * (a.bounds[9 + k] - a.bounds[6 + k]) + a.bounds[6 + k];
+        box[o][k] = tr - sz;
+        box[o][3 + k] = tr + sz;
+      }
+    }
+    __syncthreads();
+    float si = 0.f, sm_ = 0.f;
+    for (int p = tid; p < n * n; p += 128) {
+      int i = p / n, j = p % n;
+      float vi = (box[i][3] - box[i][0]) * (box[i][4] - box[i][1]) * (box[i][5] - box[i][2]);
+      float vj = (box[j][3] - box[j][0]) * (box[j][4] - box[j][1]) * (box[j][5] - box[j][2]);
+      float w0 = fmaxf(fminf(box[i][3], box[j][3]) - fmaxf(box[i][0], box[j][0]), 0.f);
+      float w1 = fmaxf(fminf(box[i][4], box[j][4]) - fmaxf(box[i][1], box[j][1]), 0.f);
+      float w2 = fmaxf(fminf(box[i][5], box[j][5]) - fmaxf(box[i][2], box[j][2]), 0.f);
+      float inter = w0 * w1 * w2;
+      float uni = fmaxf(vi + vj - inter, 1e-6f);
+      float m = valid[i] * valid[j];
+      si += inter / uni * m;
+      sm_ += m;
+    }
+    si = warp_sum(si);
+    sm_ = warp_sum(sm_);
+    if ((tid & 31) == 0) {
+      atomicAdd(&iou_acc[0], si);
+      atomicAdd(&iou_acc[1], sm_);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float* p = parts + (int64_t)b * 9;
+    const float fn = float(n);
+    float loss;
+    if (a.arrange) {
+      float ltr = acc[0] / (fn * a.trans), lan = acc[2] / (fn * a.angle);
+      loss = a.loss_separate ? ltr + lan : acc[6] / (fn * d);
+      for (int k = 0; k < 9; ++k) p[k] = 0.f;
+      p[1] = ltr;
+      p[3] = lan;
+      losses[b] = loss * loss_weight[tt];
+      return;
+    }
+    float ltr = acc[0] / (fn * a.trans), lsz = acc[1] / (fn * a.size), lan = acc[2] / (fn * a.angle);
+    float lbb = (acc[0] + acc[1] + acc[2]) / (fn * bb), lcl = acc[3] / (fn * a.cls);
+    float lob = acc[4] / (fn * (a.objn > 0 ? a.objn : 1));
+    float lof = a.feat > 0 ? acc[5] / (fn * a.feat) : 0.f;
+    if (a.loss_separate) {
+      loss = lbb + lcl;
+      if (a.objn > 0) loss += lob;
+      if (a.feat > 0) loss += lof;
+    } else {
+      loss = acc[6] / (fn * d);
+    }
+    loss *= loss_weight[tt];
+    float liou = 0.f, iou_avg = 0.f;
+    if (a.loss_iou) {
+      float den = iou_acc[1] + 1e-6f;
+      iou_avg = iou_acc[0] / den;
+      liou = alphas_cumprod[tt] * 0.1f * iou_acc[0] / den;
+      loss += liou;
+    }
+    p[0] = lbb; p[1] = ltr; p[2] = lsz; p[3] = lan; p[4] = lcl; p[5] = lob; p[6] = lof; p[7] = liou; p[8] = iou_avg;
+    losses[b] = loss;
+  }
+}
+template <typename T>
+void launch_p_losses(const float* x0, const float* noise, const float* x_t, const T* model_out, int ld_out,
+                     const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac, const float* sqrt_recip_ac,
+                     const float* sqrt_recipm1_ac, const float* loss_weight, const float* alphas_cumprod, LossArgs a,
+                     float* losses, float* parts, int B, cudaStream_t s) {
+  k_p_losses<T><<<B, 128, 0, s>>>(x0, noise, x_t, model_out, ld_out, t, sqrt_ac, sqrt_1mac, sqrt_recip_ac,
+                                  sqrt_recipm1_ac, loss_weight, alphas_cumprod, a, losses, parts);
+}
+
+__global__ void k_loss_dict_mean(const float* __restrict__ parts, float* __restrict__ dict9, int B) {
+  int k = blockIdx.x;      // 9 blocks
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += parts[(int64_t)b * 9 + k];
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) tot += red[w];
+    dict9[k] = tot / float(B);
+  }
+}
+void launch_loss_dict_mean(const float* parts, float* dict9, int B, cudaStream_t s) {
+  k_loss_dict_mean<<<9, 256, 0, s>>>(parts, dict9, B);
+}
+
+// raise the dynamic shared-memory limit of the attention cores once, outside any stream capture
+void init_pointwise_attrs() {
+  const int lim = 200 * 1024;
+  cudaFuncSetAttribute(k_linattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_linattn<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_softattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_softattn<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_xattn_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+}
+
+// ---- explicit instantiations ----
+#define INST(T)                                                                                                   \
+  template void launch_pack_input<T>(const float*, T*, int, int, int, cudaStream_t);                              \
+  template void launch_unpack_output<T>(const T*, int, float*, int, int, cudaStream_t);                           \
+  template void launch_groupnorm<T>(const T*, int, T*, int, const float*, const float*, FilmRef, const T*, int,   \
+                                    int, int, int, int, cudaStream_t);                                            \
+  template void launch_layernorm<T>(const T*, int, T*, int, const float*, const T*, int, int, int, cudaStream_t); \
+  template void launch_linattn<T>(const T*, int, T*, int, int, int, cudaStream_t);                                \
+  template void launch_softattn<T>(const T*, int, T*, int, int, int, cudaStream_t);                               \
+  template void launch_xattn_apply<T>(const T*, int, const float*, T*, int, int, int, cudaStream_t);              \
+  template void launch_step_update<T>(const StepCoef*, StepState*, float*, const T*, int, const float*, int, int, \
+                                      int, int, uint64_t, uint64_t, cudaStream_t);                                \
+  template void launch_p_sample<T>(const float*, const T*, int, const int*, const float*, float*, const float*,   \
+                                   const float*, const float*, const float*, const float*, int, int, int, int,    \
+                                   cudaStream_t);                                                                 \
+  template void launch_p_losses<T>(const float*, const float*, const float*, const T*, int, const int64_t*,       \
+                                   const float*, const float*, const float*, const float*, const float*,          \
+                                   const float*, LossArgs, float*, float*, int, cudaStream_t);
+INST(float)
+INST(bf16)
+
+}  // namespace ds

@@ -1,0 +1,50 @@
+"""CPU: the engine's step program (exported from the C++ plan builder), interpreted with torch on the CPU,
+reproduces the reference's golden denoiser outputs -- i.e. op order, buffer reuse, weight packing recipes and
+the hoisted FiLM tables are right before a single kernel runs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffuscene_b200 import capi
+from diffuscene_b200.weights import NetSpec, seeded_state_dict, unet1d_param_specs
+from oracle.plan_interp import run_plan
+from tests.cases import CASES, make_inputs
+
+
+def _run(name, no_reuse, bf16=False):
+    case = CASES[name]
+    spec = NetSpec.from_net_kwargs(case["net_kwargs"])
+    cfg = capi.make_config(spec, case["N"], case["diffusion_kwargs"]["time_num"])
+    plan = capi.plan_export(cfg, no_reuse=no_reuse)
+    sd = {k[len("diffusion.model."):]: v for k, v in
+          seeded_state_dict(unet1d_param_specs(spec), seed=case["seed"]).items()}
+    inp = make_inputs(case, spec)
+    return run_plan(plan, sd, inp["x"], inp["t"], inp["context"], inp["context_cross"], emulate_bf16=bf16)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_plan_reproduces_golden(name, golden_dir):
+    torch.set_grad_enabled(False)
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))["fwd"]
+    out = _run(name, no_reuse=False)
+    np.testing.assert_allclose(out.numpy(), gold, rtol=1e-3, atol=1e-4)    # the north-star tolerance
+    np.testing.assert_allclose(out.numpy(), gold, rtol=2e-4, atol=3e-5)    # and much tighter in practice
+
+
+def test_buffer_reuse_does_not_change_results():
+    torch.set_grad_enabled(False)
+    a = _run("bed62", no_reuse=False)
+    b = _run("bed62", no_reuse=True)
+    assert torch.equal(a, b)
+
+
+def test_bf16_emulation_error_is_bounded(golden_dir):
+    """Predicts the throughput-mode error (bf16 storage + bf16 weights, fp32 accumulate); the GPU test
+    asserts the same bound on the real kernels."""
+    torch.set_grad_enabled(False)
+    gold = torch.from_numpy(np.load(os.path.join(golden_dir, "bed62.npz"))["fwd"])
+    out = _run("bed62", no_reuse=False, bf16=True)
+    err = (out - gold).abs()
+    assert err.max() < 0.05 and err.mean() < 0.01, (err.max(), err.mean())
