@@ -17,6 +17,7 @@
 // denoise_net.py:562,566,573) is served by switching tensor maps inside the k loop.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.cuh"
@@ -36,6 +37,8 @@ struct TcEpi {
   int act;
   int M, N;
   int kb0, kb1;          // k-blocks taken from A0 and from A1
+  uint64_t desc_hi;      // constant (non-address) bits of the shared-memory matrix descriptors
+  uint32_t idesc;        // tcgen05 instruction descriptor
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,14 +90,14 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-  return d;
+__host__ __device__ constexpr uint64_t umma_desc_hi_sw128() {
+  return ((uint64_t)1 << 16)                      // leading byte offset (unused for swizzled K-major)
+         | ((uint64_t)(1024 >> 4) << 32)          // stride byte offset between 8-row groups
+         | ((uint64_t)1 << 46)                    // descriptor version (Blackwell)
+         | ((uint64_t)2 << 61);                   // SWIZZLE_128B
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint64_t hi) {
+  return hi | (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address in 16-byte units
 }
 // D(tmem, fp32) (+)= A(smem, bf16) * B(smem, bf16)^T, M = 128, N from the instruction descriptor, K = 16
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -215,12 +218,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           mbar_wait(full_bar(stage), phase, err_flag, 3);
           tc_fence_after();
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES);
+          const uint64_t adesc = umma_desc(sa, epi.desc_hi);
+          const uint64_t bdesc = umma_desc(sa + A_BYTES, epi.desc_hi);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, (kb | k) != 0);
+            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), epi.idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));          // smem slot reusable once these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
@@ -400,6 +403,11 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.N = g.N;
   p->epi.kb0 = g.k0 / BK;
   p->epi.kb1 = g.k1 / BK;
+  p->epi.desc_hi = umma_desc_hi_sw128();
+  p->epi.idesc = p->bn == 256 ? TcCfg<256>::IDESC : TcCfg<128>::IDESC;
+  // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
+  if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
+  if (const char* e = getenv("DS_TC_IDESC")) p->epi.idesc = (uint32_t)strtoul(e, nullptr, 16);
   return p;
 }
 void tc_plan_destroy(TcGemmPlan* p) { delete p; }

@@ -1,0 +1,105 @@
+"""GPU, bf16 throughput mode: tcgen05 GEMM unit tests, SIMT cross-check, error bounds against the golden
+vectors (the bound the CPU bf16 emulation in tests/test_plan_cpu.py predicts), and size-independent
+properties at BASELINE batch sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from diffuscene_b200 import capi
+from tests.cases import CASES, noise_stream
+from tests.gpu_common import cuda, get_engine, gold
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(backend, a, w, bias, act=0):
+    lib = capi.load()
+    M, K = a.shape
+    N = w.shape[0]
+    d = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    capi.check(lib.ds_test_gemm_bf16(backend, a.data_ptr(), w.data_ptr(), None if bias is None else bias.data_ptr(),
+                                     d.data_ptr(), M, N, K, act, None))
+    return d
+
+
+@pytest.mark.parametrize("backend", [capi.DS_GEMM_SIMT, capi.DS_GEMM_TCGEN05], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 256, 128), (1000, 512, 512), (3001, 384, 512),
+                                   (5000, 1536, 64), (777, 512, 3072), (40000, 1024, 512)])
+def test_gemm_matches_torch(backend, shape):
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = a.float() @ w.float().t() + bias
+    for act, fn in ((0, lambda z: z), (1, torch.nn.functional.gelu)):
+        d = _gemm(backend, a, w, bias, act).float()
+        r = fn(ref)
+        err = (d - r).abs().max().item()
+        assert err <= 2e-2 * max(1.0, r.abs().max().item()), (shape, act, err)
+        # bf16 output rounding only: relative error of a bf16 ulp
+        assert ((d - r).abs() <= 8e-3 * r.abs() + 2e-3).all()
+
+
+@pytest.mark.parametrize("backend", ["simt", "tcgen05"])
+@pytest.mark.parametrize("name", ["bed62", "bed97", "liv65", "text62", "arr5", "obj29"])
+def test_forward_error_bound(name, backend, golden_dir):
+    eng, case, spec, inp = get_engine(name, "bf16", backend)
+    g = torch.from_numpy(gold(golden_dir, name)["fwd"])
+    out = eng.forward(cuda(inp["x"]), cuda(inp["t"])).cpu()
+    err = (out - g).abs()
+    # bf16 storage + bf16 weights, fp32 accumulate: the reference probe saw max 1.8e-3
+    assert err.max() < 1e-2 and err.mean() < 2e-3, (err.max().item(), err.mean().item())
+    if spec.seperate_all:
+        b0 = spec.bbox_dim
+        agree = (out[..., b0:b0 + spec.class_dim - 1].argmax(-1) == g[..., b0:b0 + spec.class_dim - 1].argmax(-1))
+        assert agree.float().mean() >= 0.9
+
+
+def test_tcgen05_agrees_with_simt_bf16():
+    """Same bf16 inputs, fp32 accumulation in both: only the summation order differs."""
+    e1, case, spec, inp = get_engine("bed62", "bf16", "tcgen05")
+    e2, _, _, _ = get_engine("bed62", "bf16", "simt")
+    a = e1.forward(cuda(inp["x"]), cuda(inp["t"]))
+    b = e2.forward(cuda(inp["x"]), cuda(inp["t"]))
+    assert (a - b).abs().max().item() < 3e-3
+
+
+def test_sampling_loop_bf16_close_to_fp32_reference(golden_dir):
+    eng, case, spec, inp = get_engine("bed62_loop", "bf16", "tcgen05")
+    g = gold(golden_dir, "bed62_loop")
+    T = case["diffusion_kwargs"]["time_num"]
+    shape = tuple(inp["x"].shape)
+    nz = noise_stream(case["seed"] + 100)
+    x_T = nz(shape)
+    noise = torch.stack([nz(shape) for _ in range(T)])
+    out = eng.sample(shape[0], clip_denoised=True, x_init=x_T, noise=noise).cpu().numpy()
+    assert np.abs(out - g["loop"]).max() < 5e-2
+
+
+def test_batch_independence_at_full_size():
+    """Size-independent property at BASELINE batch (4096 scenes): a scene's result does not depend on what
+    else is in the batch (tiles never mix scenes), so the first rows of a big batch equal a small batch."""
+    eng, case, spec, inp = get_engine("bed62", "bf16", "tcgen05")
+    B = 4096
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(B, case["N"], spec.point_dim, generator=g).cuda()
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    big = eng.forward(x, t)
+    small = eng.forward(x[:5].contiguous(), t[:5].contiguous())
+    assert torch.isfinite(big).all()
+    assert torch.equal(big[:5], small)
+    # permuting scenes permutes outputs
+    perm = torch.randperm(B, generator=g).cuda()
+    assert torch.equal(eng.forward(x[perm].contiguous(), t[perm].contiguous()), big[perm])
+
+
+def test_full_sample_smoke_bf16():
+    eng, case, spec, inp = get_engine("bed62_loop", "bf16", "tcgen05")
+    out = eng.sample(256, seed=11)
+    assert torch.isfinite(out).all()
+    out_h = eng.sample(256, seed=11, host_output=True)
+    assert torch.equal(out_h, out.cpu())
