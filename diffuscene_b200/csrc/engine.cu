@@ -85,6 +85,23 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // ------------------------------------------------------------------------------------------------
 // op execution
 // ------------------------------------------------------------------------------------------------
+static FilmRef film_ref(ds_handle* h, const Op& o) {
+  const Plan& P = h->plan;
+  const int C = P.C;
+  FilmRef f;
+  f.base = nullptr; f.mode = FILM_NONE; f.row_stride = 0; f.t = h->t_dev;
+  if (o.film == 1) {
+    f.base = h->time_table + (size_t)o.film_blk * 2 * C;
+    f.mode = FILM_TIME;
+    f.row_stride = (int64_t)P.time_blocks.size() * 2 * C;
+  } else if (o.film == 2) {
+    f.base = h->ctx_table ? h->ctx_table + (size_t)o.film_blk * 2 * C : nullptr;
+    f.mode = h->ctx_shared ? FILM_OBJECT : FILM_TOKEN;
+    f.row_stride = (int64_t)P.ctx_blocks.size() * 2 * C;
+  }
+  return f;
+}
+
 template <typename T>
 static int run_op(ds_handle* h, int idx, int n_scenes, cudaStream_t s) {
   const Plan& P = h->plan;
@@ -95,6 +112,9 @@ static int run_op(ds_handle* h, int idx, int n_scenes, cudaStream_t s) {
   switch (o.kind) {
     case OP_PACK:
       return DS_ERR_STATE;   // handled by the caller (needs the x pointer)
+    case OP_GEMM_GN:
+      if (!h->use_tc) return fail(DS_ERR_STATE, "fused GroupNorm op without the tcgen05 backend");
+      // fallthrough
     case OP_GEMM: {
       if (h->use_tc) {
         int e = launch_gemm_tc(h->tc[idx], M, s);
@@ -102,6 +122,7 @@ static int run_op(ds_handle* h, int idx, int n_scenes, cudaStream_t s) {
                            cudaGetErrorString((cudaError_t)e));
       } else {
         GemmArgs g;
+        memset(&g, 0, sizeof g);
         g.a0 = ptr(o.in0.buf, o.in0.col); g.lda0 = ld(o.in0.buf); g.k0 = o.in0.k;
         g.a1 = ptr(o.in1.buf, o.in1.col); g.lda1 = ld(o.in1.buf); g.k1 = o.in1.buf >= 0 ? o.in1.k : 0;
         g.w = h->warena + h->w_off[o.w]; g.ldw = P.wmats[o.w].K;
@@ -114,17 +135,7 @@ static int run_op(ds_handle* h, int idx, int n_scenes, cudaStream_t s) {
       break;
     }
     case OP_GN: {
-      FilmRef f;
-      f.base = nullptr; f.mode = FILM_NONE; f.row_stride = 0; f.t = h->t_dev;
-      if (o.film == 1) {
-        f.base = h->time_table + (size_t)o.film_blk * 2 * C;
-        f.mode = FILM_TIME;
-        f.row_stride = (int64_t)P.time_blocks.size() * 2 * C;
-      } else if (o.film == 2) {
-        f.base = h->ctx_table + (size_t)o.film_blk * 2 * C;
-        f.mode = h->ctx_shared ? FILM_OBJECT : FILM_TOKEN;
-        f.row_stride = (int64_t)P.ctx_blocks.size() * 2 * C;
-      }
+      FilmRef f = film_ref(h, o);
       launch_groupnorm<T>(ptr(o.in0.buf, 0), ld(o.in0.buf), ptr(o.out, 0), ld(o.out), h->varena + h->v_off[o.gamma],
                           h->varena + h->v_off[o.beta], f, ptr(o.res, 0), ld(o.res), n_scenes, n_obj, C, 8, s);
       break;
@@ -209,9 +220,16 @@ static int ensure_capacity(ds_handle* h, int n_scenes) {
   if (h->use_tc) {
     for (size_t i = 0; i < P.ops.size(); ++i) {
       const Op& o = P.ops[i];
-      if (o.kind != OP_GEMM) continue;
+      if (o.kind != OP_GEMM && o.kind != OP_GEMM_GN) continue;
       auto ptr = [&](int buf, int col) -> bf16* { return buf < 0 ? nullptr : (bf16*)h->bufs[buf] + col; };
       GemmArgs g;
+      memset(&g, 0, sizeof g);
+      if (o.kind == OP_GEMM_GN) {
+        g.gn = 1; g.n_obj = n_obj; g.film_C = P.C;
+        g.gamma = h->varena + h->v_off[o.gamma];
+        g.beta = h->varena + h->v_off[o.beta];
+        g.film = film_ref(h, o);
+      }
       g.a0 = ptr(o.in0.buf, o.in0.col); g.lda0 = P.buf_width[o.in0.buf]; g.k0 = o.in0.k;
       g.a1 = ptr(o.in1.buf, o.in1.col); g.lda1 = o.in1.buf >= 0 ? P.buf_width[o.in1.buf] : 0;
       g.k1 = o.in1.buf >= 0 ? o.in1.k : 0;
@@ -558,6 +576,8 @@ extern "C" int ds_set_context(ds_handle* h, const float* context_dev, int32_t ba
   h->ctx_shared = shared != 0;
   h->ctx_batch = shared ? 0 : batch;
   h->ctx_set = true;
+  for (size_t i = 0; i < h->tc.size(); ++i)     // fused epilogues carry the table pointer / mode
+    if (h->tc[i] && P.ops[i].kind == OP_GEMM_GN && P.ops[i].film == 2) tc_plan_set_film(h->tc[i], film_ref(h, P.ops[i]));
   if (!stream) CK(cudaStreamSynchronize(s));
   return 0;
 }

@@ -4,14 +4,21 @@
 // This kernel carries every 1x1-conv / linear layer of the denoiser in throughput mode (reference:
 // F.conv1d / nn.Linear calls of scene_synthesis/networks/denoise_net.py:91,183,214-217,244-245,487-502).
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A (128 x 64) and W (BN x 64)
 //               into a STAGES-deep shared-memory ring, completion on mbarriers
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block,
 //               accumulating into one of two TMEM buffers; tcgen05.commit releases smem slots / signals
 //               the epilogue
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> bf16 -> HBM;
-//               double-buffered TMEM lets the epilogue of tile i overlap the MMAs of tile i+1
+//   warps 2-9   epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns):
+//               tcgen05.ld (32 lanes x 32 columns) -> epilogue math -> bf16 -> HBM; double-buffered TMEM
+//               lets the epilogue of tile i overlap the MMAs of tile i+1.  Two epilogues:
+//                 plain  bias / GELU|SiLU / residual
+//                 GN     the whole `Block` of the reference (denoise_net.py:160-176) after the conv:
+//                        bias -> GroupNorm(8) statistics per (scene, group) reduced across the rows of a
+//                        scene through shared memory -> affine -> FiLM -> SiLU (-> + residual).  M tiles
+//                        are whole scenes (120 of 128 rows for N=12, 126 for N=21), N tiles are 4 whole
+//                        groups, so the statistics never leave the CTA.
 // Both operands are K-major (activations [rows, K], weights [N, K] exactly as PyTorch stores them), so no
 // transposes exist anywhere in the data path.  A "virtual concat" [A0|A1] (the U-Net skip connections,
 // denoise_net.py:562,566,573) is served by switching tensor maps inside the k loop.
@@ -26,7 +33,8 @@ namespace ds {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int TC_THREADS = 192;
+static constexpr int EPI_WARPS = 8;
+static constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 static constexpr uint64_t WAIT_TIMEOUT_CYCLES = 4000000000ull;   // ~2 s: a protocol bug traps instead of hanging
 
@@ -39,6 +47,13 @@ struct TcEpi {
   int kb0, kb1;          // k-blocks taken from A0 and from A1
   uint64_t desc_hi;      // constant (non-address) bits of the shared-memory matrix descriptors
   uint32_t idesc;        // tcgen05 instruction descriptor
+  int tile_rows;         // rows advanced per M tile (128, or whole scenes for the GN epilogue)
+  // GroupNorm epilogue
+  int n_obj;             // rows per scene
+  int C;                 // channel count of the FiLM table rows ([scale(C) | shift(C)])
+  const float* gamma;
+  const float* beta;
+  FilmRef film;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +103,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
 __host__ __device__ constexpr uint64_t umma_desc_hi_sw128() {
@@ -125,6 +141,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2  (one MUFU op; |rel err| ~ 2^-11, below the bf16 output ulp)
+__device__ __forceinline__ float silu_tanh(float x) {
+  float h = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 template <int BN>
 struct TcCfg {
@@ -132,27 +154,37 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers (256 or 512 columns)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue scratch: per-column constants (bias, gamma, beta, -) + GroupNorm partials and statistics
+  static constexpr int CHAN_BYTES = BN * 16;
+  static constexpr int PART_BYTES = BM * 4 * 8;
+  static constexpr int STAT_BYTES = BM * 4 * 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CHAN_BYTES +
+                                    PART_BYTES + STAT_BYTES;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
                                     (uint32_t(BM >> 4) << 24);
 };
 
-template <int BN>
+template <int BN, bool GN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
           const __grid_constant__ CUtensorMap tm_w, TcEpi epi, int* err_flag) {
   using Cfg = TcCfg<BN>;
+  static_assert(!GN || BN == 256, "the GroupNorm epilogue owns 4 groups of 64 channels per tile");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* const scratch = base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 256;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
+  float4* const chan = reinterpret_cast<float4*>(scratch);                              // [BN] (bias, gamma, beta, 0)
+  float2* const part = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES);            // [128 rows][4 groups]
+  float2* const stat = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES);   // [scene][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -166,7 +198,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+      mbar_init(tempty_bar(b), EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -182,7 +214,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_m = (epi.M + BM - 1) / BM;
+  const int num_m = (epi.M + epi.tile_rows - 1) / epi.tile_rows;
   const int num_n = epi.N / BN;
   const int total = num_m * num_n;
   const int kblocks = epi.kb0 + epi.kb1;
@@ -193,12 +225,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int m_idx = tile % num_m, n_idx = tile / num_m;
+        const int m0 = m_idx * epi.tile_rows;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          if (kb < epi.kb0) tma_load_2d(sa, &tm_a0, kb * BK, m_idx * BM, full_bar(stage));
-          else tma_load_2d(sa, &tm_a1, (kb - epi.kb0) * BK, m_idx * BM, full_bar(stage));
+          if (kb < epi.kb0) tma_load_2d(sa, &tm_a0, kb * BK, m0, full_bar(stage));
+          else tma_load_2d(sa, &tm_a1, (kb - epi.kb0) * BK, m0, full_bar(stage));
           tma_load_2d(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN, full_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -233,35 +266,115 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       }
     }
   } else {
+    // ---------------- epilogue warps ----------------
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int hh = (warp - 2) >> 2;                // which half of the tile's columns this warp owns
+    const int etid = threadIdx.x - 64;             // 0..255
     const int row_in_tile = q * 32 + lane;
+    constexpr int HALF = BN / 2;
+    constexpr int CHUNKS = HALF / 32;
     int ab = 0;
     uint32_t aphase = 0;
+    // GN: row -> (scene slot, row in scene); constant per thread
+    const int sc_local = GN ? row_in_tile / epi.n_obj : 0;
+    const int r_in_scene = GN ? row_in_tile - sc_local * epi.n_obj : 0;
+    const int scenes_per_tile = GN ? epi.tile_rows / epi.n_obj : 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int m_idx = tile % num_m, n_idx = tile / num_m;
-      const int m = m_idx * BM + row_in_tile;
+      const int m0 = m_idx * epi.tile_rows;
+      const int m = m0 + row_in_tile;
+      const bool row_ok = row_in_tile < epi.tile_rows && m < epi.M;
+      // stage the per-column constants of this N tile (previous tile's readers are past their last barrier)
+      epi_bar_sync();
+      if (etid < BN) {
+        const int n = n_idx * BN + etid;
+        float4 c4;
+        c4.x = epi.bias ? __ldg(epi.bias + n) : 0.f;
+        c4.y = GN ? __ldg(epi.gamma + n) : 1.f;
+        c4.z = GN ? __ldg(epi.beta + n) : 0.f;
+        c4.w = 0.f;
+        chan[etid] = c4;
+      }
+      epi_bar_sync();
       mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN);
+      const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN + hh * HALF);
+
+      if constexpr (GN) {
+        // pass 1: per-row partial sums of the two 64-channel groups this warp owns
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+        for (int g = 0; g < 2; ++g) {
+          float s = 0.f, ss = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr0 + uint32_t(g * 64 + c * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]) + chan[hh * HALF + g * 64 + c * 32 + j].x;
+              s += v;
+              ss = fmaf(v, v, ss);
+            }
+          }
+          part[row_in_tile * 4 + hh * 2 + g] = make_float2(s, ss);
+        }
+        epi_bar_sync();
+        if (etid < scenes_per_tile * 4) {
+          const int sc = etid >> 2, g = etid & 3;
+          float s = 0.f, ss = 0.f;
+          for (int r = 0; r < epi.n_obj; ++r) {
+            float2 p2 = part[(sc * epi.n_obj + r) * 4 + g];
+            s += p2.x;
+            ss += p2.y;
+          }
+          const float inv = 1.0f / float(epi.n_obj * 64);
+          const float mean = s * inv;
+          const float var = fmaxf(ss * inv - mean * mean, 0.f);
+          stat[etid] = make_float2(mean, rsqrtf(var + 1e-5f));
+        }
+        epi_bar_sync();
+      }
+
+      const float* frow = nullptr;
+      if (GN && row_ok && epi.film.mode != FILM_NONE) {
+        const int scene_g = m_idx * scenes_per_tile + sc_local;
+        if (epi.film.mode == FILM_TIME) frow = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
+        else if (epi.film.mode == FILM_OBJECT) frow = epi.film.base + (int64_t)r_in_scene * epi.film.row_stride;
+        else frow = epi.film.base + (int64_t)m * epi.film.row_stride;
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr0 + uint32_t(c * 32), r);
-        if (m < epi.M) {
-          const int n0 = n_idx * BN + c * 32;
+        if (row_ok) {
+          const int cl = hh * HALF + c * 32;          // column within the tile
+          const int n0 = n_idx * BN + cl;             // global output column
           float v[32];
+          if constexpr (GN) {
+            const float2 st = stat[sc_local * 4 + (cl >> 6)];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (epi.bias) {
+            for (int j = 0; j < 32; ++j) {
+              const float4 c4 = chan[cl + j];
+              float y = (__uint_as_float(r[j]) + c4.x - st.x) * st.y;
+              v[j] = fmaf(y, c4.y, c4.z);
+            }
+            if (frow) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(epi.bias + n0 + j);
-          }
-          if (epi.act == ACT_GELU) {
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
+            }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (epi.act == ACT_SILU) {
+            for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + chan[cl + j].x;
+            if (epi.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (epi.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+            }
           }
           if (epi.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(epi.res + (int64_t)m * epi.ldres + n0);
@@ -311,6 +424,7 @@ struct TcGemmPlan {
   CUtensorMap tm_a0, tm_a1, tm_w;
   TcEpi epi;
   int bn;
+  bool gn;
   int num_sms;
 };
 
@@ -343,8 +457,9 @@ bool tc_runtime_available(char* err, int err_len) {
     cudaHostAlloc((void**)&g_err_flag, sizeof(int), cudaHostAllocMapped);
     *g_err_flag = 0;
   }
-  cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
   return true;
 }
@@ -380,10 +495,16 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     if (err) snprintf(err, err_len, "tcgen05 GEMM needs 16-byte aligned operands and pitches");
     return nullptr;
   }
+  const bool gn = g.gn != 0;
+  if (gn && (g.N % 256 || g.n_obj < 1 || g.n_obj > 128 || !g.gamma || !g.beta)) {
+    if (err) snprintf(err, err_len, "fused GroupNorm epilogue needs N%%256==0, 1<=n_obj<=128, gamma/beta");
+    return nullptr;
+  }
   TcGemmPlan* p = new TcGemmPlan();
   memset(p, 0, sizeof(*p));
   // BN = 256 halves the A re-reads; keep 128 when N is not a multiple of 256
   p->bn = (g.N % 256 == 0) ? 256 : 128;
+  p->gn = gn;
   p->num_sms = g_num_sms;
   bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, BM, err, err_len);
   if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, BM, err, err_len);
@@ -405,26 +526,35 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.kb1 = g.k1 / BK;
   p->epi.desc_hi = umma_desc_hi_sw128();
   p->epi.idesc = p->bn == 256 ? TcCfg<256>::IDESC : TcCfg<128>::IDESC;
+  p->epi.tile_rows = gn ? (BM / g.n_obj) * g.n_obj : BM;
+  p->epi.n_obj = g.n_obj;
+  p->epi.C = g.film_C;
+  p->epi.gamma = g.gamma;
+  p->epi.beta = g.beta;
+  p->epi.film = g.film;
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
   if (const char* e = getenv("DS_TC_IDESC")) p->epi.idesc = (uint32_t)strtoul(e, nullptr, 16);
   return p;
 }
 void tc_plan_destroy(TcGemmPlan* p) { delete p; }
+void tc_plan_set_film(TcGemmPlan* p, const FilmRef& f) { p->epi.film = f; }
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   TcEpi epi = p->epi;
   epi.M = M;
-  const int num_m = (M + BM - 1) / BM;
+  const int num_m = (M + epi.tile_rows - 1) / epi.tile_rows;
   const int total = num_m * (epi.N / p->bn);
   if (total == 0) return 0;
   const int grid = total < p->num_sms ? total : p->num_sms;
   int* flag_dev = nullptr;
   cudaHostGetDevicePointer((void**)&flag_dev, g_err_flag, 0);
-  if (p->bn == 256)
-    k_gemm_tc<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+  if (p->gn)
+    k_gemm_tc<256, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+  else if (p->bn == 256)
+    k_gemm_tc<256, false><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
   else
-    k_gemm_tc<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+    k_gemm_tc<128, false><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
   return (int)cudaPeekAtLastError();
 }
 

@@ -96,6 +96,13 @@ struct GemmArgs {
   void* d; int ldd;
   const void* res; int ldres;            // optional residual added after the activation
   int M, N, act;
+  // fused GroupNorm(8 groups) + affine + FiLM + SiLU epilogue (tcgen05 backend only)
+  int gn;
+  int n_obj;
+  int film_C;
+  const float* gamma;
+  const float* beta;
+  FilmRef film;
 };
 template <typename T> void launch_gemm_simt(const GemmArgs& g, bool exact, cudaStream_t s);
 // fp32 A/W in, fp32 out (time / context FiLM tables; always fp32)
@@ -105,6 +112,7 @@ void launch_gemm_f32(const GemmArgs& g, cudaStream_t s);
 struct TcGemmPlan;   // opaque, owns tensor maps
 TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int err_len);
 void tc_plan_destroy(TcGemmPlan* p);
+void tc_plan_set_film(TcGemmPlan* p, const FilmRef& f);   // FiLM tables may be (re)allocated after planning
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s);   // returns 0 or cudaError
 bool tc_runtime_available(char* err, int err_len);
 

@@ -11,6 +11,7 @@ namespace {
 struct Builder {
   Plan* p;
   bool no_reuse;
+  bool fuse = false;
   std::vector<int> refs;
   std::map<int, std::vector<int>> free_by_width;
   int C;
@@ -84,6 +85,42 @@ struct Builder {
       p->ctx_blocks.push_back(name);
       expect(name + ".mlp.1.weight", int64_t(2 * C) * p->cfg.cond_dim);
       expect(name + ".mlp.1.bias", 2 * C);
+    }
+    if (fuse) {
+      // Block = conv -> GroupNorm -> FiLM -> SiLU as ONE kernel (GEMM with the GroupNorm epilogue)
+      int h1 = new_buf(C);
+      {
+        Op o;
+        o.kind = OP_GEMM_GN; o.name = name + ".block1"; o.in0 = a0; o.in1 = a1; o.out = h1; o.N = C;
+        o.w = wsingle(name + ".block1.proj.weight", C, cin, true);
+        o.b = vsingle(name + ".block1.proj.bias", C);
+        o.gamma = vsingle(name + ".block1.norm.weight", C);
+        o.beta = vsingle(name + ".block1.norm.bias", C);
+        o.film = film; o.film_blk = film_blk;
+        p->ops.push_back(o);
+      }
+      int rs;
+      if (cin != C) {
+        rs = new_buf(C);
+        gemm(name + ".res_conv", a0, a1, wsingle(name + ".res_conv.weight", C, cin),
+             vsingle(name + ".res_conv.bias", C), C, 0, -1, rs, 0);
+      } else {
+        rs = a0.buf;
+        retain(rs);
+      }
+      int out = new_buf(C);
+      {
+        Op o;
+        o.kind = OP_GEMM_GN; o.name = name; o.in0 = full(h1); o.out = out; o.N = C; o.res = rs;
+        o.w = wsingle(name + ".block2.proj.weight", C, C, true);
+        o.b = vsingle(name + ".block2.proj.bias", C);
+        o.gamma = vsingle(name + ".block2.norm.weight", C);
+        o.beta = vsingle(name + ".block2.norm.bias", C);
+        p->ops.push_back(o);
+      }
+      release(h1);
+      release(rs);
+      return out;
     }
     int t1 = new_buf(C);
     gemm(name + ".block1.proj", a0, a1, wsingle(name + ".block1.proj.weight", C, cin, true),
@@ -242,6 +279,7 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
   b.p = &P;
   b.no_reuse = no_reuse;
   b.C = C;
+  b.fuse = cfg.fuse_level >= 1 && cfg.precision == DS_PREC_BF16 && cfg.gemm_backend != DS_GEMM_SIMT && C % 256 == 0;
 
   // ---- input + encoder ----
   int xin = b.new_buf(P.kin_pad);
@@ -392,7 +430,7 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
 }
 
 std::string describe_plan(const Plan& p) {
-  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN"};
+  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN", "GEMM_GN"};
   std::ostringstream os;
   os << "plan: C=" << p.C << " d=" << p.d << " kin_pad=" << p.kin_pad << " dpad=" << p.dpad << " buffers="
      << p.buf_width.size() << " ops=" << p.ops.size() << " time_blocks=" << p.time_blocks.size()
@@ -400,11 +438,12 @@ std::string describe_plan(const Plan& p) {
   for (size_t i = 0; i < p.ops.size(); ++i) {
     const Op& o = p.ops[i];
     os << i << " " << kinds[o.kind] << " " << o.name;
-    if (o.kind == OP_GEMM) {
+    if (o.kind == OP_GEMM || o.kind == OP_GEMM_GN) {
       os << " K=" << (o.in0.k + o.in1.k) << " N=" << o.N << " a0=b" << o.in0.buf << "[" << o.in0.col << ":" << o.in0.k
          << "]";
       if (o.in1.buf >= 0) os << " a1=b" << o.in1.buf;
       os << " act=" << o.act;
+      if (o.film) os << " film=" << o.film << ":" << o.film_blk;
     } else {
       os << " in=b" << o.in0.buf;
       if (o.film) os << " film=" << o.film << ":" << o.film_blk;

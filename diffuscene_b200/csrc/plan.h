@@ -25,6 +25,7 @@ enum OpKind {
   OP_LINATTN,       // linear-attention core on qkv [M, 384] -> [M, 128]
   OP_ATTN,          // softmax-attention core
   OP_XATTN,         // cross linear-attention apply (q [M,128] x precomputed text context)
+  OP_GEMM_GN,       // GEMM with the GroupNorm + affine (+FiLM) + SiLU (+res) epilogue fused (tcgen05 only)
 };
 
 struct Slice { int buf = -1; int col = 0; int k = 0; };

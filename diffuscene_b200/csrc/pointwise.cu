@@ -135,11 +135,92 @@ __global__ void __launch_bounds__(128) k_layernorm(const T* __restrict__ in, int
     }
   }
 }
+// C == 512 fast path: each lane owns 16 contiguous channels (two 16-byte loads for bf16, four for fp32)
+template <typename T> struct Vec16;
+template <> struct Vec16<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[16]) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 pk = q[h];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h2[e]);
+        v[h * 8 + e * 2] = f.x;
+        v[h * 8 + e * 2 + 1] = f.y;
+      }
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[16]) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 pk;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[h * 8 + e * 2], v[h * 8 + e * 2 + 1]);
+      q[h] = pk;
+    }
+  }
+};
+template <> struct Vec16<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[16]) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float4 f = q[h];
+      v[h * 4] = f.x; v[h * 4 + 1] = f.y; v[h * 4 + 2] = f.z; v[h * 4 + 3] = f.w;
+    }
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[16]) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) q[h] = make_float4(v[h * 4], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+  }
+};
+
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(256) k_layernorm512(const T* __restrict__ in, int ld_in, T* __restrict__ out,
+                                                      int ld_out, const float* __restrict__ g,
+                                                      const T* __restrict__ res, int ld_res, int M) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float v[16];
+  Vec16<T>::load(in + row * ld_in + lane * 16, v);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / 512.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float dlt = v[i] - mean;
+    q = fmaf(dlt, dlt, q);
+  }
+  const float var = warp_sum(q) * (1.0f / 512.0f);
+  const float rstd = EXACT ? 1.0f / sqrtf(var + 1e-5f) : rsqrtf(var + 1e-5f);
+  float gg[16];
+  Vec16<float>::load(g + lane * 16, gg);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (v[i] - mean) * rstd * gg[i];
+  if (res) {
+    float r[16];
+    Vec16<T>::load(res + row * ld_res + lane * 16, r);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += r[i];
+  }
+  Vec16<T>::store(out + row * ld_out + lane * 16, v);
+}
+
 template <typename T>
 void launch_layernorm(const T* in, int ld_in, T* out, int ld_out, const float* g, const T* res, int ld_res, int M,
                       int C, cudaStream_t s) {
   constexpr bool EX = sizeof(T) == 4;
-  k_layernorm<T, EX><<<cdiv(M, 4), 128, 0, s>>>(in, ld_in, out, ld_out, g, res, ld_res, M, C);
+  const bool vec_ok = C == 512 && ld_in % 16 == 0 && ld_out % 16 == 0 && (!res || ld_res % 16 == 0);
+  if (vec_ok) k_layernorm512<T, EX><<<cdiv(M, 8), 256, 0, s>>>(in, ld_in, out, ld_out, g, res, ld_res, M);
+  else k_layernorm<T, EX><<<cdiv(M, 4), 128, 0, s>>>(in, ld_in, out, ld_out, g, res, ld_res, M, C);
 }
 
 // ------------------------------------------------------------------------------------------------

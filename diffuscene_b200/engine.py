@@ -29,7 +29,7 @@ class DenoiserEngine:
     """One Unet1D + diffusion schedule on one GPU (reference: DiffusionPoint, diffusion_ddpm.py:721-803)."""
 
     def __init__(self, spec: NetSpec, num_objects: int, num_timesteps: int, precision: str = "bf16",
-                 gemm_backend: str = "auto", device: int = 0, fuse_level: int = 0):
+                 gemm_backend: str = "auto", device: int = 0, fuse_level: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("diffuscene_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = capi.load()
@@ -38,6 +38,9 @@ class DenoiserEngine:
         self.num_timesteps = num_timesteps
         self.precision = precision
         self.device = torch.device("cuda", device)
+        if fuse_level is None:      # fused GEMM epilogues exist for the tcgen05 path only
+            fuse_level = 1 if (precision == "bf16" and gemm_backend != "simt") else 0
+        self.fuse_level = fuse_level
         self.cfg = capi.make_config(spec, num_objects, num_timesteps, _PREC[precision], _BACKEND[gemm_backend],
                                     device, fuse_level)
         h = C.c_void_p()

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .unet1d_ref import sinusoidal_embedding
 
-OP_PACK, OP_GEMM, OP_GN, OP_LN, OP_LINATTN, OP_ATTN, OP_XATTN = range(7)
+OP_PACK, OP_GEMM, OP_GN, OP_LN, OP_LINATTN, OP_ATTN, OP_XATTN, OP_GEMM_GN = range(8)
 
 
 def _r(x, on):
@@ -79,7 +79,7 @@ def run_plan(plan: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.
             bufs[op["out"]] = _r(out, bf)
             continue
         i0 = op["in0"]
-        if k == OP_GEMM:
+        if k == OP_GEMM or k == OP_GEMM_GN:
             a = bufs[i0["buf"]][:, i0["col"]:i0["col"] + i0["k"]]
             if op["in1"]["buf"] >= 0:
                 i1 = op["in1"]
@@ -87,6 +87,22 @@ def run_plan(plan: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.
             y = a @ wm[op["w"]].t()
             if op["b"] >= 0:
                 y = y + vecs[op["b"]]
+        if k == OP_GEMM_GN:      # the GEMM result stays in fp32 (TMEM) through the GroupNorm epilogue
+            h = y.reshape(B, N, 8, C // 8)
+            mean = h.mean(dim=(1, 3), keepdim=True)
+            var = h.var(dim=(1, 3), unbiased=False, keepdim=True)
+            y = ((h - mean) * torch.rsqrt(var + 1e-5)).reshape(B, N, C) * vecs[op["gamma"]] + vecs[op["beta"]]
+            if op["film"] == 1:
+                f = film_t[op["film_blk"]][:, None, :]
+                y = y * (f[..., :C] + 1) + f[..., C:]
+            elif op["film"] == 2:
+                f = film_c[op["film_blk"]].reshape(B, N, 2 * C)
+                y = y * (f[..., :C] + 1) + f[..., C:]
+            y = F.silu(y).reshape(M, C)
+            if op["res"] >= 0:
+                y = y + bufs[op["res"]]
+            bufs[op["out"]] = _r(y, bf)
+        elif k == OP_GEMM:
             if op["act"] == 1:
                 y = F.gelu(y)
             elif op["act"] == 2:

@@ -18,14 +18,14 @@ def case_tables(case):
     return make_tables(betas, dk["model_mean_type"], dk["model_var_type"])
 
 
-def get_engine(name, precision="fp32", backend="auto"):
-    key = (name, precision, backend)
+def get_engine(name, precision="fp32", backend="auto", fuse=None):
+    key = (name, precision, backend, fuse)
     if key in _ENGINES:
         return _ENGINES[key]
     case = CASES[name]
     spec = NetSpec.from_net_kwargs(case["net_kwargs"])
     eng = DenoiserEngine(spec, case["N"], case["diffusion_kwargs"]["time_num"], precision=precision,
-                         gemm_backend=backend)
+                         gemm_backend=backend, fuse_level=fuse)
     eng.load_state_dict(seeded_state_dict(unet1d_param_specs(spec), seed=case["seed"]))
     eng.set_schedule(case_tables(case))
     inp = make_inputs(case, spec)

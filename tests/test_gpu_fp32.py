@@ -121,11 +121,13 @@ def test_intermediate_taps_match_plan_interpreter():
         M = case["B"] * case["N"]
         bad = []
         for op in plan["ops"]:
-            if op["kind"] == 0 or op["out_col"] != 0:
+            if op["kind"] == 0:
                 continue
             got = eng.read_tap(op["name"], M)
             ref = taps[op["name"]]
-            err = (got[:, :ref.shape[1]] - ref).abs().max().item()
+            c0, c1 = op["out_col"], op["out_col"] + (op["N"] if op["kind"] == 1 else ref.shape[1])
+            got, ref = got[:, c0:c1], ref[:, c0:c1]      # grouped GEMMs fill column blocks of a shared buffer
+            err = (got - ref).abs().max().item()
             if err > 2e-3 * max(1.0, ref.abs().max().item()):
                 bad.append((op["name"], err))
         assert not bad, bad[:10]

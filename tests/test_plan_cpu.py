@@ -13,10 +13,10 @@ from oracle.plan_interp import run_plan
 from tests.cases import CASES, make_inputs
 
 
-def _run(name, no_reuse, bf16=False):
+def _run(name, no_reuse, bf16=False, fuse=0):
     case = CASES[name]
     spec = NetSpec.from_net_kwargs(case["net_kwargs"])
-    cfg = capi.make_config(spec, case["N"], case["diffusion_kwargs"]["time_num"])
+    cfg = capi.make_config(spec, case["N"], case["diffusion_kwargs"]["time_num"], fuse_level=fuse)
     plan = capi.plan_export(cfg, no_reuse=no_reuse)
     sd = {k[len("diffusion.model."):]: v for k, v in
           seeded_state_dict(unet1d_param_specs(spec), seed=case["seed"]).items()}
@@ -31,6 +31,19 @@ def test_plan_reproduces_golden(name, golden_dir):
     out = _run(name, no_reuse=False)
     np.testing.assert_allclose(out.numpy(), gold, rtol=1e-3, atol=1e-4)    # the north-star tolerance
     np.testing.assert_allclose(out.numpy(), gold, rtol=2e-4, atol=3e-5)    # and much tighter in practice
+
+
+@pytest.mark.parametrize("name", ["bed62", "liv65", "text62", "arr5"])
+def test_fused_plan_reproduces_golden(name, golden_dir):
+    """fuse_level 1: every Block (conv+GroupNorm+FiLM+SiLU) is one GEMM_GN op."""
+    torch.set_grad_enabled(False)
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))["fwd"]
+    out = _run(name, no_reuse=False, fuse=1)
+    np.testing.assert_allclose(out.numpy(), gold, rtol=2e-4, atol=3e-5)
+    case = CASES[name]
+    cfg = capi.make_config(NetSpec.from_net_kwargs(case["net_kwargs"]), case["N"], 1000, fuse_level=1)
+    txt = capi.plan_describe(cfg)
+    assert " GN " not in txt and txt.count(" GEMM_GN ") == 56
 
 
 def test_buffer_reuse_does_not_change_results():
