@@ -121,7 +121,7 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         self._param_names: List[str] = []
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())      # follows torch.manual_seed like nn init does
         for name, shape, kind in unet1d_param_specs(self.spec):
-            _register(self, name, nn.Parameter(seeded_tensor(name, shape, kind, seed)))
+            _register(self, name, nn.Parameter(seeded_tensor(name, shape, kind, seed, perturb_norms=False)))
             self._param_names.append(name)
 
         dk = dict(config["diffusion_kwargs"])

