@@ -106,7 +106,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 32)      # torch CPU ops of this size stop scaling (and oversubscribe) beyond ~32 threads
     batch, dsteps = 32, 2
     vals = []
     for i in range(args.warmup + args.steps):
@@ -243,7 +243,7 @@ def main():
             for n, u in ops:
                 sys.stderr.write("  %-40s %8.1f\n" % (n, u))
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = min(os.cpu_count() or 1, 32)
             v, dt = oracle_scenes_per_sec(16, 3, threads)
             res["cpu_baseline"] = {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port",
                                    "sample": "3 diffusion steps x 16 scenes (oracle, fp32 torch CPU), scaled to 1000 steps"}

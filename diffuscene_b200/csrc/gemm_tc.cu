@@ -141,6 +141,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // x * sigmoid(x) = h + h * tanh(h), h = x / 2  (one MUFU op; |rel err| ~ 2^-11, below the bf16 output ulp)
 __device__ __forceinline__ float silu_tanh(float x) {
   float h = 0.5f * x, t;
@@ -148,18 +161,33 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
-template <int BN>
+// GELU in its tanh form (max |deviation| from the erf form ~3e-4, below the bf16 output ulp for |x| > 0.1):
+// 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  -- throughput mode only; the fp32 parity path uses erff
+__device__ __forceinline__ float gelu_tanh(float x) {
+  float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f), t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+
+template <int BN, bool GN>
 struct TcCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers (256 or 512 columns)
   // epilogue scratch: per-column constants (bias, gamma, beta, -) + GroupNorm partials and statistics
-  static constexpr int CHAN_BYTES = BN * 16;
-  static constexpr int PART_BYTES = BM * 4 * 8;
-  static constexpr int STAT_BYTES = BM * 4 * 8;
+  // per-column constants for ALL N columns of the GEMM, staged once per CTA:
+  //   GN: float4 (bias, gamma, beta, -) for N <= 512;  plain: float bias for N <= 4096
+  static constexpr int CHAN_MAX_N = GN ? 512 : 4096;
+  static constexpr int CHAN_BYTES = GN ? CHAN_MAX_N * 16 : CHAN_MAX_N * 4;
+  static constexpr int PART_BYTES = GN ? BM * 4 * 8 : 0;
+  static constexpr int STAT_BYTES = BM * 4 * 8;          // generic path: up to 128 scenes per tile
+  static constexpr int SPT_FAST = 10;                    // folded-coefficient fast path: <= 10 scenes per tile
+  static constexpr int AB_BYTES = BN * SPT_FAST * 8;     // aliases STAT (fast path needs SPT_FAST*4 stats only)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CHAN_BYTES +
-                                    PART_BYTES + STAT_BYTES;
+                                    (GN ? PART_BYTES + 512 + (AB_BYTES > STAT_BYTES ? AB_BYTES : STAT_BYTES) : 0);
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
                                     (uint32_t(BM >> 4) << 24);
@@ -169,7 +197,7 @@ template <int BN, bool GN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
           const __grid_constant__ CUtensorMap tm_w, TcEpi epi, int* err_flag) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, GN>;
   static_assert(!GN || BN == 256, "the GroupNorm epilogue owns 4 groups of 64 channels per tile");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -182,9 +210,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
   uint8_t* const scratch = base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 256;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
-  float4* const chan = reinterpret_cast<float4*>(scratch);                              // [BN] (bias, gamma, beta, 0)
+  float4* const chan = reinterpret_cast<float4*>(scratch);          // GN: [N] (bias, gamma, beta, 0)
+  float* const bias_s = reinterpret_cast<float*>(scratch);          // plain: [N] bias
   float2* const part = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES);            // [128 rows][4 groups]
   float2* const stat = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES);   // [scene][4]
+  // fast path: stats live in the first 512 bytes, the folded (A, B) coefficients [col][scene] after them;
+  // generic path (many small scenes per tile): the whole region is the stat table
+  float2* const coef = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -224,7 +256,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m_idx = tile % num_m, n_idx = tile / num_m;
+        const int n_idx = tile % num_n, m_idx = tile / num_n;   // N fastest: CTAs that run together share the A tile in L2
         const int m0 = m_idx * epi.tile_rows;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
@@ -279,44 +311,88 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     const int sc_local = GN ? row_in_tile / epi.n_obj : 0;
     const int r_in_scene = GN ? row_in_tile - sc_local * epi.n_obj : 0;
     const int scenes_per_tile = GN ? epi.tile_rows / epi.n_obj : 0;
+    // stage the per-column constants once per CTA
+    for (int n = etid; n < epi.N; n += EPI_WARPS * 32) {
+      if constexpr (GN) {
+        chan[n] = make_float4(epi.bias ? __ldg(epi.bias + n) : 0.f, __ldg(epi.gamma + n), __ldg(epi.beta + n), 0.f);
+      } else {
+        bias_s[n] = epi.bias ? __ldg(epi.bias + n) : 0.f;
+      }
+    }
+    epi_bar_sync();
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int m_idx = tile % num_m, n_idx = tile / num_m;
+      const int n_idx = tile % num_n, m_idx = tile / num_n;   // N fastest: CTAs that run together share the A tile in L2
       const int m0 = m_idx * epi.tile_rows;
       const int m = m0 + row_in_tile;
       const bool row_ok = row_in_tile < epi.tile_rows && m < epi.M;
-      // stage the per-column constants of this N tile (previous tile's readers are past their last barrier)
-      epi_bar_sync();
-      if (etid < BN) {
-        const int n = n_idx * BN + etid;
-        float4 c4;
-        c4.x = epi.bias ? __ldg(epi.bias + n) : 0.f;
-        c4.y = GN ? __ldg(epi.gamma + n) : 1.f;
-        c4.z = GN ? __ldg(epi.beta + n) : 0.f;
-        c4.w = 0.f;
-        chan[etid] = c4;
-      }
-      epi_bar_sync();
       mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN + hh * HALF);
 
+      // residual (prefetched one chunk ahead) add + bf16 pack + 64-byte store of 32 consecutive columns of a row
+      auto load_res = [&](uint4 (&rv)[4], int n0) {
+        if (epi.res && row_ok) {
+          const uint4* rp = reinterpret_cast<const uint4*>(epi.res + (int64_t)m * epi.ldres + n0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
+        }
+      };
+      auto store_chunk = [&](float (&v)[32], const uint4 (&rv)[4], int n0) {
+        if (epi.res) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h2[e]);
+              v[g * 8 + e * 2] += f.x;
+              v[g * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        uint4* dp = reinterpret_cast<uint4*>(epi.d + (int64_t)m * epi.ldd + n0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
+          dp[g] = pk;
+        }
+      };
+      const int nbase = n_idx * BN + hh * HALF;     // first global column this warp owns in this tile
+      uint4 res_a[4], res_b[4];
+      load_res(res_a, nbase);                       // chunk 0 residual in flight during the statistics pass
+
       if constexpr (GN) {
-        // pass 1: per-row partial sums of the two 64-channel groups this warp owns
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
+        // ---- pass 1: per-row partial (sum, sum of squares) of the two 64-channel groups this warp owns;
+        //      TMEM loads are software-pipelined (next chunk in flight while this one is reduced)
+        {
+          uint32_t ra[32], rb[32];
           float s = 0.f, ss = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(taddr0 + uint32_t(g * 64 + c * 32), r);
+          auto acc = [&](const uint32_t (&r)[32], int coff) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]) + chan[hh * HALF + g * 64 + c * 32 + j].x;
+              float v = __uint_as_float(r[j]) + chan[n_idx * BN + hh * HALF + coff + j].x;
               s += v;
               ss = fmaf(v, v, ss);
             }
-          }
-          part[row_in_tile * 4 + hh * 2 + g] = make_float2(s, ss);
+          };
+          tmem_ld32_issue(taddr0, ra);
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 32u, rb);
+          acc(ra, 0);
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 64u, ra);
+          acc(rb, 32);
+          part[row_in_tile * 4 + hh * 2] = make_float2(s, ss);
+          s = 0.f; ss = 0.f;
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 96u, rb);
+          acc(ra, 64);
+          tmem_ld_wait();
+          acc(rb, 96);
+          part[row_in_tile * 4 + hh * 2 + 1] = make_float2(s, ss);
         }
         epi_bar_sync();
         if (etid < scenes_per_tile * 4) {
@@ -333,71 +409,132 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           stat[etid] = make_float2(mean, rsqrtf(var + 1e-5f));
         }
         epi_bar_sync();
-      }
 
-      const float* frow = nullptr;
-      if (GN && row_ok && epi.film.mode != FILM_NONE) {
-        const int scene_g = m_idx * scenes_per_tile + sc_local;
-        if (epi.film.mode == FILM_TIME) frow = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
-        else if (epi.film.mode == FILM_OBJECT) frow = epi.film.base + (int64_t)r_in_scene * epi.film.row_stride;
-        else frow = epi.film.base + (int64_t)m * epi.film.row_stride;
-      }
-
+        const bool fast = scenes_per_tile <= Cfg::SPT_FAST &&
+                          (epi.film.mode == FILM_NONE || epi.film.mode == FILM_TIME);
+        if (fast) {
+          // ---- fold bias, statistics, affine and (per-scene) FiLM into y = acc * A + B per (column, scene)
+          {
+            const int col = etid;                      // 256 epilogue threads <-> 256 tile columns
+            const int n = n_idx * BN + col;
+            const float4 c4 = chan[n];
+            const int n_scenes_total = epi.M / epi.n_obj;
+            for (int sc = 0; sc < scenes_per_tile; ++sc) {
+              const float2 st = stat[sc * 4 + (col >> 6)];
+              float a = st.y * c4.y;
+              float b = fmaf(c4.x - st.x, a, c4.z);
+              const int scene_g = m_idx * scenes_per_tile + sc;
+              if (epi.film.mode == FILM_TIME && scene_g < n_scenes_total) {
+                const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
+                const float s1 = __ldg(fr + n) + 1.0f;
+                b = fmaf(b, s1, __ldg(fr + epi.C + n));
+                a *= s1;
+              }
+              coef[col * scenes_per_tile + sc] = make_float2(a, b);
+            }
+          }
+          epi_bar_sync();
+          // ---- pass 2: one FMA + SiLU per element
+          uint32_t ra[32], rb[32];
+          const float2* cb = coef + (hh * HALF) * scenes_per_tile + sc_local;
+          auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
+            if (c + 1 < CHUNKS) load_res(rnext, nbase + (c + 1) * 32);
+            if (row_ok) {
+              float v[32];
+              const float2* cc = cb + c * 32 * scenes_per_tile;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float2 k2 = cc[j * scenes_per_tile];
+                v[j] = silu_tanh(fmaf(__uint_as_float(r[j]), k2.x, k2.y));
+              }
+              store_chunk(v, rcur, nbase + c * 32);
+            }
+          };
+          tmem_ld32_issue(taddr0, ra);
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 32u, rb);
+          finish(ra, 0, res_a, res_b);
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 64u, ra);
+          finish(rb, 1, res_b, res_a);
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 96u, rb);
+          finish(ra, 2, res_a, res_b);
+          tmem_ld_wait();
+          finish(rb, 3, res_b, res_a);
+        } else {
+          // ---- generic pass 2: per-object / per-token FiLM rows (context blocks), or many scenes per tile
+          const float* frow = nullptr;
+          if (row_ok && epi.film.mode != FILM_NONE) {
+            const int scene_g = m_idx * scenes_per_tile + sc_local;
+            if (epi.film.mode == FILM_TIME) frow = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
+            else if (epi.film.mode == FILM_OBJECT) frow = epi.film.base + (int64_t)r_in_scene * epi.film.row_stride;
+            else frow = epi.film.base + (int64_t)m * epi.film.row_stride;
+          }
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr0 + uint32_t(c * 32), r);
-        if (row_ok) {
-          const int cl = hh * HALF + c * 32;          // column within the tile
-          const int n0 = n_idx * BN + cl;             // global output column
-          float v[32];
-          if constexpr (GN) {
-            const float2 st = stat[sc_local * 4 + (cl >> 6)];
+          for (int c = 0; c < CHUNKS; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr0 + uint32_t(c * 32), r);
+            if (row_ok) {
+              const int cl = hh * HALF + c * 32;          // column within the tile
+              const int n0 = n_idx * BN + cl;             // global output column
+              float v[32];
+              const float2 st = stat[sc_local * 4 + (cl >> 6)];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float4 c4 = chan[cl + j];
-              float y = (__uint_as_float(r[j]) + c4.x - st.x) * st.y;
-              v[j] = fmaf(y, c4.y, c4.z);
+              for (int j = 0; j < 32; ++j) {
+                const float4 c4 = chan[n0 + j];
+                float y = (__uint_as_float(r[j]) + c4.x - st.x) * st.y;
+                v[j] = fmaf(y, c4.y, c4.z);
+              }
+              if (frow) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
+              if (c > 0) load_res(res_a, n0);
+              store_chunk(v, res_a, n0);
             }
-            if (frow) {
+          }
+        }
+      } else {
+        // ---- plain epilogue: bias, activation, residual (TMEM loads software-pipelined)
+        uint32_t ra[32], rb[32];
+        auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
+          if (c + 1 < CHUNKS) load_res(rnext, nbase + (c + 1) * 32);
+          if (row_ok) {
+            const int cl = hh * HALF + c * 32;
+            float v[32];
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n_idx * BN + cl);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + chan[cl + j].x;
             if (epi.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
             } else if (epi.act == ACT_SILU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
             }
+            store_chunk(v, rcur, n_idx * BN + cl);
           }
-          if (epi.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(epi.res + (int64_t)m * epi.ldres + n0);
+        };
+        tmem_ld32_issue(taddr0, ra);
+        tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 pk = __ldg(rp + g);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(h2[e]);
-                v[g * 8 + e * 2] += f.x;
-                v[g * 8 + e * 2 + 1] += f.y;
-              }
-            }
-          }
-          uint4* dp = reinterpret_cast<uint4*>(epi.d + (int64_t)m * epi.ldd + n0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 pk;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
-            dp[g] = pk;
+        for (int c = 0; c < CHUNKS; c += 2) {
+          if (c + 1 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 1) * 32), rb);
+          finish(ra, c, res_a, res_b);
+          if (c + 1 < CHUNKS) {
+            tmem_ld_wait();
+            if (c + 2 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 2) * 32), ra);
+            finish(rb, c + 1, res_b, res_a);
+            if (c + 2 < CHUNKS) tmem_ld_wait();
           }
         }
       }
@@ -457,9 +594,9 @@ bool tc_runtime_available(char* err, int err_len) {
     cudaHostAlloc((void**)&g_err_flag, sizeof(int), cudaHostAllocMapped);
     *g_err_flag = 0;
   }
-  cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
   return true;
 }
@@ -496,8 +633,12 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     return nullptr;
   }
   const bool gn = g.gn != 0;
-  if (gn && (g.N % 256 || g.n_obj < 1 || g.n_obj > 128 || !g.gamma || !g.beta)) {
-    if (err) snprintf(err, err_len, "fused GroupNorm epilogue needs N%%256==0, 1<=n_obj<=128, gamma/beta");
+  if (gn && (g.N % 256 || g.N > TcCfg<256, true>::CHAN_MAX_N || g.n_obj < 1 || g.n_obj > 128 || !g.gamma || !g.beta)) {
+    if (err) snprintf(err, err_len, "fused GroupNorm epilogue needs N%%256==0, N<=512, 1<=n_obj<=128, gamma/beta");
+    return nullptr;
+  }
+  if (!gn && g.N > TcCfg<256, false>::CHAN_MAX_N) {
+    if (err) snprintf(err, err_len, "tcgen05 GEMM supports N <= 4096 (N=%d)", g.N);
     return nullptr;
   }
   TcGemmPlan* p = new TcGemmPlan();
@@ -525,7 +666,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.kb0 = g.k0 / BK;
   p->epi.kb1 = g.k1 / BK;
   p->epi.desc_hi = umma_desc_hi_sw128();
-  p->epi.idesc = p->bn == 256 ? TcCfg<256>::IDESC : TcCfg<128>::IDESC;
+  p->epi.idesc = p->bn == 256 ? TcCfg<256, false>::IDESC : TcCfg<128, false>::IDESC;
   p->epi.tile_rows = gn ? (BM / g.n_obj) * g.n_obj : BM;
   p->epi.n_obj = g.n_obj;
   p->epi.C = g.film_C;
@@ -550,11 +691,11 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   int* flag_dev = nullptr;
   cudaHostGetDevicePointer((void**)&flag_dev, g_err_flag, 0);
   if (p->gn)
-    k_gemm_tc<256, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+    k_gemm_tc<256, true><<<grid, TC_THREADS, TcCfg<256, true>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
   else if (p->bn == 256)
-    k_gemm_tc<256, false><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+    k_gemm_tc<256, false><<<grid, TC_THREADS, TcCfg<256, false>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
   else
-    k_gemm_tc<128, false><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+    k_gemm_tc<128, false><<<grid, TC_THREADS, TcCfg<128, false>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
   return (int)cudaPeekAtLastError();
 }
 
