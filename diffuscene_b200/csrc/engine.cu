@@ -1044,6 +1044,43 @@ extern "C" int ds_profile_ops(ds_handle* h, int32_t batch, char* names_buf, int6
   return n;
 }
 
+// Bring-up aid: one tcgen05 GEMM (optionally with the GroupNorm epilogue, n_obj > 0) with per-role cycle counters.
+// trace_host receives [148][8] uint64 (see gemm_tc.cu for the slot meaning); reps launches are timed with events.
+extern "C" int ds_test_gemm_trace(const void* a_dev, const void* w_dev, const float* bias_dev, const void* res_dev,
+                                  void* d_dev, int32_t M, int32_t N, int32_t K, int32_t n_obj, const float* gamma_dev,
+                                  const float* beta_dev, int32_t reps, unsigned long long* trace_host, float* usec) {
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.a0 = a_dev; g.lda0 = K; g.k0 = K; g.w = w_dev; g.ldw = K; g.bias = bias_dev; g.d = d_dev; g.ldd = N;
+  g.res = res_dev; g.ldres = N; g.M = M; g.N = N;
+  if (n_obj > 0) { g.gn = 1; g.n_obj = n_obj; g.film_C = N; g.gamma = gamma_dev; g.beta = beta_dev; g.film.mode = FILM_NONE; }
+  char err[256] = "";
+  TcGemmPlan* p = tc_plan_create(g, M, err, sizeof err);
+  if (!p) return fail(DS_ERR_CUDA, "%s", err);
+  unsigned long long* tr = nullptr;
+  CK(cudaMalloc(&tr, 256 * 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(tr, 0, 256 * 8 * sizeof(unsigned long long)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) launch_gemm_tc(p, M, 0);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < reps; ++i) launch_gemm_tc(p, M, 0);
+  cudaEventRecord(e1, 0);
+  cudaError_t se = cudaDeviceSynchronize();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (usec) *usec = ms * 1000.f / reps;
+  tc_plan_set_trace(p, tr);
+  launch_gemm_tc(p, M, 0);
+  se = cudaDeviceSynchronize();
+  if (trace_host) cudaMemcpy(trace_host, tr, 256 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(tr);
+  tc_plan_destroy(p);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (se != cudaSuccess) return fail(DS_ERR_CUDA, "trace GEMM failed: %s (code %d)", cudaGetErrorString(se), tc_error_flag());
+  return 0;
+}
+
 extern "C" int ds_test_gemm_bf16(int backend, const void* a_dev, const void* w_dev, const float* bias_dev, void* d_dev,
                                  int32_t M, int32_t N, int32_t K, int32_t act, void* stream) {
   GemmArgs g;

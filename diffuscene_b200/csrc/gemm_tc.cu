@@ -54,7 +54,10 @@ struct TcEpi {
   const float* gamma;
   const float* beta;
   FilmRef film;
+  unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
 };
+// trace slots: 0 producer wait-empty, 1 producer total, 2 mma wait-tmem-empty, 3 mma wait-full, 4 mma total,
+//              5 epilogue(warp 2) wait-tmem-full, 6 epilogue total, 7 tiles processed
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -97,6 +100,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -127,6 +152,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -219,6 +250,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   float2* const coef = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // thread-block cluster: the CS CTAs of a cluster work on CS consecutive M tiles of the same N tile and share
+  // the weight tile -- each CTA loads 1/CS of it and multicasts the slice into every CTA's shared memory
+  const uint32_t cs = cluster_nctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint16_t cmask = uint16_t((1u << cs) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a0);
@@ -226,7 +262,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     tma_prefetch_desc(&tm_w);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), cs);       // every CTA of the cluster must have consumed the slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -243,30 +279,46 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();        // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int num_m = (epi.M + epi.tile_rows - 1) / epi.tile_rows;
   const int num_n = epi.N / BN;
-  const int total = num_m * num_n;
+  const int num_mg = (num_m + int(cs) - 1) / int(cs);          // groups of CS consecutive M tiles
+  const int total = num_mg * num_n;                             // cluster tiles
+  const int cluster_id = blockIdx.x / cs, num_clusters = gridDim.x / cs;
   const int kblocks = epi.kb0 + epi.kb1;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int n_idx = tile % num_n, m_idx = tile / num_n;   // N fastest: CTAs that run together share the A tile in L2
+      unsigned long long tw = 0, tstart = clock64();
+      for (int tile = cluster_id; tile < total; tile += num_clusters) {
+        const int n_idx = tile % num_n, m_idx = (tile / num_n) * int(cs) + int(crank);   // N fastest: neighbours share A in L2
         const int m0 = m_idx * epi.tile_rows;
         for (int kb = 0; kb < kblocks; ++kb) {
+          unsigned long long t0 = epi.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
+          if (epi.trace) tw += clock64() - t0;
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
           if (kb < epi.kb0) tma_load_2d(sa, &tm_a0, kb * BK, m0, full_bar(stage));
           else tma_load_2d(sa, &tm_a1, (kb - epi.kb0) * BK, m0, full_bar(stage));
-          tma_load_2d(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN, full_bar(stage));
+          if (cs == 1) {
+            tma_load_2d(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN, full_bar(stage));
+          } else {
+            const int rows = BN / int(cs);      // this CTA's slice of the weight tile, broadcast to the cluster
+            tma_load_2d_mc(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), &tm_w, kb * BK,
+                           n_idx * BN + int(crank) * rows, full_bar(stage), cmask);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (epi.trace) {
+        epi.trace[blockIdx.x * 8 + 0] = tw;
+        epi.trace[blockIdx.x * 8 + 1] = clock64() - tstart;
       }
     }
   } else if (warp == 1) {
@@ -275,12 +327,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       uint32_t phase = 0;
       int ab = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      unsigned long long tw_te = 0, tw_f = 0, tstart = clock64();
+      for (int tile = cluster_id; tile < total; tile += num_clusters) {
+        unsigned long long t0 = epi.trace ? clock64() : 0;
         mbar_wait(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
+        if (epi.trace) tw_te += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(ab * BN);
         for (int kb = 0; kb < kblocks; ++kb) {
+          t0 = epi.trace ? clock64() : 0;
           mbar_wait(full_bar(stage), phase, err_flag, 3);
+          if (epi.trace) tw_f += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = umma_desc(sa, epi.desc_hi);
@@ -290,11 +347,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
             umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), epi.idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));          // smem slot reusable once these MMAs have read it
+          if (cs == 1) umma_commit(empty_bar(stage));     // smem slot reusable once these MMAs have read it
+          else umma_commit_mc(empty_bar(stage), cmask);   // ... in every CTA of the cluster
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(ab));               // accumulator complete -> epilogue
         if (++ab == 2) { ab = 0; aphase ^= 1u; }
+      }
+      if (epi.trace) {
+        epi.trace[blockIdx.x * 8 + 2] = tw_te;
+        epi.trace[blockIdx.x * 8 + 3] = tw_f;
+        epi.trace[blockIdx.x * 8 + 4] = clock64() - tstart;
       }
     }
   } else {
@@ -320,12 +383,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       }
     }
     epi_bar_sync();
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int n_idx = tile % num_n, m_idx = tile / num_n;   // N fastest: CTAs that run together share the A tile in L2
+    unsigned long long tw_tf = 0, tstart = clock64(), ntiles = 0;
+    for (int tile = cluster_id; tile < total; tile += num_clusters) {
+      const int n_idx = tile % num_n, m_idx = (tile / num_n) * int(cs) + int(crank);   // N fastest: neighbours share A in L2
       const int m0 = m_idx * epi.tile_rows;
       const int m = m0 + row_in_tile;
       const bool row_ok = row_in_tile < epi.tile_rows && m < epi.M;
+      unsigned long long t0 = epi.trace ? clock64() : 0;
       mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
+      if (epi.trace) { tw_tf += clock64() - t0; ++ntiles; }
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN + hh * HALF);
 
@@ -543,10 +609,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       if (lane == 0) mbar_arrive(tempty_bar(ab));
       if (++ab == 2) { ab = 0; aphase ^= 1u; }
     }
+    if (epi.trace && warp == 2 && lane == 0) {
+      epi.trace[blockIdx.x * 8 + 5] = tw_tf;
+      epi.trace[blockIdx.x * 8 + 6] = clock64() - tstart;
+      epi.trace[blockIdx.x * 8 + 7] = ntiles;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();        // no CTA leaves while peers may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
@@ -563,6 +635,8 @@ struct TcGemmPlan {
   int bn;
   bool gn;
   int num_sms;
+  int cluster;       // CTAs per cluster (weight-tile multicast width): 1, 2 or 4
+  int max_clusters;  // co-resident clusters of that size
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -650,7 +724,10 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, BM, err, err_len);
   if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, BM, err, err_len);
   if (ok && !g.a1) p->tm_a1 = p->tm_a0;
-  if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, p->bn, err, err_len);
+  p->cluster = 1;
+  if (const char* e = getenv("DS_TC_CLUSTER")) p->cluster = atoi(e);
+  if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) p->cluster = 1;
+  if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, p->bn / p->cluster, err, err_len);
   if (!ok) {
     delete p;
     return nullptr;
@@ -680,23 +757,50 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
 }
 void tc_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_plan_set_film(TcGemmPlan* p, const FilmRef& f) { p->epi.film = f; }
+void tc_plan_set_trace(TcGemmPlan* p, unsigned long long* trace) { p->epi.trace = trace; }
+
+template <int BN, bool GN>
+static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* flag_dev, cudaStream_t s) {
+  const int cs = p->cluster;
+  int max_cl = p->num_sms / cs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<BN, GN>::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cs > 1) {
+    static int cached[3][5] = {{0}};      // [kernel variant][cluster size]
+    const int kv = GN ? 2 : (BN == 256 ? 1 : 0);
+    if (!cached[kv][cs]) {
+      cfg.gridDim = dim3(p->num_sms / cs * cs);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc<BN, GN>, &cfg) == cudaSuccess && n > 0) cached[kv][cs] = n;
+      else cached[kv][cs] = max_cl;
+    }
+    if (cached[kv][cs] < max_cl) max_cl = cached[kv][cs];
+  }
+  const int ncl = total_ct < max_cl ? total_ct : max_cl;
+  cfg.gridDim = dim3(ncl * cs);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+}
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   TcEpi epi = p->epi;
   epi.M = M;
   const int num_m = (M + epi.tile_rows - 1) / epi.tile_rows;
-  const int total = num_m * (epi.N / p->bn);
-  if (total == 0) return 0;
-  const int grid = total < p->num_sms ? total : p->num_sms;
+  const int total_ct = ((num_m + p->cluster - 1) / p->cluster) * (epi.N / p->bn);
+  if (total_ct == 0) return 0;
   int* flag_dev = nullptr;
   cudaHostGetDevicePointer((void**)&flag_dev, g_err_flag, 0);
-  if (p->gn)
-    k_gemm_tc<256, true><<<grid, TC_THREADS, TcCfg<256, true>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
-  else if (p->bn == 256)
-    k_gemm_tc<256, false><<<grid, TC_THREADS, TcCfg<256, false>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
-  else
-    k_gemm_tc<128, false><<<grid, TC_THREADS, TcCfg<128, false>::SMEM_BYTES, s>>>(p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
-  return (int)cudaPeekAtLastError();
+  if (p->gn) return launch_one<256, true>(p, epi, total_ct, flag_dev, s);
+  if (p->bn == 256) return launch_one<256, false>(p, epi, total_ct, flag_dev, s);
+  return launch_one<128, false>(p, epi, total_ct, flag_dev, s);
 }
 
 int tc_error_flag() { return g_err_flag ? *g_err_flag : 0; }

@@ -187,6 +187,12 @@ DS_API int ds_profile_ops(ds_handle* h, int32_t batch, char* names_buf, int64_t 
 DS_API int ds_test_gemm_bf16(int backend, const void* a_dev, const void* w_dev, const float* bias_dev, void* d_dev,
                       int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
 
+/* Bring-up / profiling aid: one tcgen05 GEMM (GroupNorm epilogue when n_obj > 0) timed with CUDA events over
+ * `reps` launches, plus per-role cycle counters of one traced launch: trace_host[256][8] uint64. */
+DS_API int ds_test_gemm_trace(const void* a_dev, const void* w_dev, const float* bias_dev, const void* res_dev,
+                              void* d_dev, int32_t M, int32_t N, int32_t K, int32_t n_obj, const float* gamma_dev,
+                              const float* beta_dev, int32_t reps, unsigned long long* trace_host, float* usec);
+
 #ifdef __cplusplus
 }
 #endif
