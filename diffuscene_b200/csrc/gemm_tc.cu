@@ -108,6 +108,15 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -205,7 +214,7 @@ template <int BN, bool GN>
 struct TcCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = GN ? 3 : ((BN == 256) ? 4 : 6);
   static constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers (256 or 512 columns)
   // epilogue scratch: per-column constants (bias, gamma, beta, -) + GroupNorm partials and statistics
   // per-column constants for ALL N columns of the GEMM, staged once per CTA:
@@ -213,11 +222,13 @@ struct TcCfg {
   static constexpr int CHAN_MAX_N = GN ? 512 : 4096;
   static constexpr int CHAN_BYTES = GN ? CHAN_MAX_N * 16 : CHAN_MAX_N * 4;
   static constexpr int PART_BYTES = GN ? BM * 4 * 8 : 0;
-  static constexpr int STAT_BYTES = BM * 4 * 8;          // generic path: up to 128 scenes per tile
   static constexpr int SPT_FAST = 10;                    // folded-coefficient fast path: <= 10 scenes per tile
-  static constexpr int AB_BYTES = BN * SPT_FAST * 8;     // aliases STAT (fast path needs SPT_FAST*4 stats only)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CHAN_BYTES +
-                                    (GN ? PART_BYTES + 512 + (AB_BYTES > STAT_BYTES ? AB_BYTES : STAT_BYTES) : 0);
+  static constexpr int AB_BYTES = BN * SPT_FAST * 8;     // folded (A, B) coefficients [column][scene]
+  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 64;   // per epilogue warp: 32 rows x 32 bf16, 64B-swizzled
+  static constexpr int GN_BYTES = GN ? PART_BYTES + 512 + AB_BYTES : 0;
+  static constexpr int SCRATCH_OFF = STAGES * STAGE_BYTES + 256;          // barriers occupy the 256 bytes before it
+  static constexpr int STAGING_OFF = ((SCRATCH_OFF + CHAN_BYTES + GN_BYTES + 1023) / 1024) * 1024;   // swizzle-atom aligned
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGING_OFF + STAGING_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
@@ -227,7 +238,8 @@ struct TcCfg {
 template <int BN, bool GN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
-          const __grid_constant__ CUtensorMap tm_w, TcEpi epi, int* err_flag) {
+          const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_d,
+          const __grid_constant__ CUtensorMap tm_dt, TcEpi epi, int* err_flag) {
   using Cfg = TcCfg<BN, GN>;
   static_assert(!GN || BN == 256, "the GroupNorm epilogue owns 4 groups of 64 channels per tile");
   extern __shared__ uint8_t smem_raw[];
@@ -239,15 +251,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
-  uint8_t* const scratch = base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 256;
+  uint8_t* const scratch = base_ptr + Cfg::SCRATCH_OFF;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   float4* const chan = reinterpret_cast<float4*>(scratch);          // GN: [N] (bias, gamma, beta, 0)
   float* const bias_s = reinterpret_cast<float*>(scratch);          // plain: [N] bias
   float2* const part = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES);            // [128 rows][4 groups]
   float2* const stat = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES);   // [scene][4]
-  // fast path: stats live in the first 512 bytes, the folded (A, B) coefficients [col][scene] after them;
-  // generic path (many small scenes per tile): the whole region is the stat table
-  float2* const coef = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512);
+  float2* const coef = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512);   // [col][scene]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // thread-block cluster: the CS CTAs of a cluster work on CS consecutive M tiles of the same N tile and share
@@ -260,6 +270,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     tma_prefetch_desc(&tm_a0);
     tma_prefetch_desc(&tm_a1);
     tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_d);
+    tma_prefetch_desc(&tm_dt);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), cs);       // every CTA of the cluster must have consumed the slot
@@ -395,7 +407,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN + hh * HALF);
 
-      // residual (prefetched one chunk ahead) add + bf16 pack + 64-byte store of 32 consecutive columns of a row
+      const int nbase = n_idx * BN + hh * HALF;     // first global column this warp owns in this tile
+      uint4 res_a[4], res_b[4];
       auto load_res = [&](uint4 (&rv)[4], int n0) {
         if (epi.res && row_ok) {
           const uint4* rp = reinterpret_cast<const uint4*>(epi.res + (int64_t)m * epi.ldres + n0);
@@ -403,63 +416,70 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
         }
       };
-      auto store_chunk = [&](float (&v)[32], const uint4 (&rv)[4], int n0) {
-        if (epi.res) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __bfloat1622float2(h2[e]);
-              v[g * 8 + e * 2] += f.x;
-              v[g * 8 + e * 2 + 1] += f.y;
-            }
-          }
-        }
-        uint4* dp = reinterpret_cast<uint4*>(epi.d + (int64_t)m * epi.ldd + n0);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
-          dp[g] = pk;
-        }
-      };
-      const int nbase = n_idx * BN + hh * HALF;     // first global column this warp owns in this tile
-      uint4 res_a[4], res_b[4];
-      load_res(res_a, nbase);                       // chunk 0 residual in flight during the statistics pass
+      load_res(res_a, nbase);                       // chunk 0 residual in flight while the accumulator is read
 
-      if constexpr (GN) {
-        // ---- pass 1: per-row partial (sum, sum of squares) of the two 64-channel groups this warp owns;
-        //      TMEM loads are software-pipelined (next chunk in flight while this one is reduced)
-        {
-          uint32_t ra[32], rb[32];
-          float s = 0.f, ss = 0.f;
-          auto acc = [&](const uint32_t (&r)[32], int coff) {
+      // ---- pass 1: read the accumulator ONCE (software-pipelined TMEM loads), add the bias, apply the plain
+      //      activation or accumulate GroupNorm partial sums, keep the values as packed bf16 in registers, and
+      //      hand the TMEM buffer back to the MMA warp before any of the slow work (statistics, stores) starts
+      uint32_t pk[CHUNKS][16];
+      float gs[2] = {0.f, 0.f}, gss[2] = {0.f, 0.f};
+      {
+        uint32_t ra[32], rb[32];
+        auto take = [&](const uint32_t (&r)[32], int c) {
+          float v[32];
+          if constexpr (GN) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]) + chan[n_idx * BN + hh * HALF + coff + j].x;
-              s += v;
-              ss = fmaf(v, v, ss);
+              v[j] = __uint_as_float(r[j]) + chan[nbase + c * 32 + j].x;
+              gs[c >> 1] += v[j];
+              gss[c >> 1] = fmaf(v[j], v[j], gss[c >> 1]);
             }
-          };
-          tmem_ld32_issue(taddr0, ra);
-          tmem_ld_wait();
-          tmem_ld32_issue(taddr0 + 32u, rb);
-          acc(ra, 0);
-          tmem_ld_wait();
-          tmem_ld32_issue(taddr0 + 64u, ra);
-          acc(rb, 32);
-          part[row_in_tile * 4 + hh * 2] = make_float2(s, ss);
-          s = 0.f; ss = 0.f;
-          tmem_ld_wait();
-          tmem_ld32_issue(taddr0 + 96u, rb);
-          acc(ra, 64);
-          tmem_ld_wait();
-          acc(rb, 96);
-          part[row_in_tile * 4 + hh * 2 + 1] = make_float2(s, ss);
+          } else {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            }
+            if (epi.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+            } else if (epi.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[c][j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        };
+        tmem_ld32_issue(taddr0, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < CHUNKS; c += 2) {
+          if (c + 1 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 1) * 32), rb);
+          take(ra, c);
+          if (c + 1 < CHUNKS) {
+            tmem_ld_wait();
+            if (c + 2 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 2) * 32), ra);
+            take(rb, c + 1);
+            if (c + 2 < CHUNKS) tmem_ld_wait();
+          }
         }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(ab));   // accumulator buffer free: the next tile's MMAs may start
+      if (++ab == 2) { ab = 0; aphase ^= 1u; }
+
+      if constexpr (GN) {
+        part[row_in_tile * 4 + hh * 2] = make_float2(gs[0], gss[0]);
+        part[row_in_tile * 4 + hh * 2 + 1] = make_float2(gs[1], gss[1]);
         epi_bar_sync();
         if (etid < scenes_per_tile * 4) {
           const int sc = etid >> 2, g = etid & 3;
@@ -475,140 +495,100 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           stat[etid] = make_float2(mean, rsqrtf(var + 1e-5f));
         }
         epi_bar_sync();
-
-        const bool fast = scenes_per_tile <= Cfg::SPT_FAST &&
-                          (epi.film.mode == FILM_NONE || epi.film.mode == FILM_TIME);
-        if (fast) {
-          // ---- fold bias, statistics, affine and (per-scene) FiLM into y = acc * A + B per (column, scene)
-          {
-            const int col = etid;                      // 256 epilogue threads <-> 256 tile columns
-            const int n = n_idx * BN + col;
-            const float4 c4 = chan[n];
-            const int n_scenes_total = epi.M / epi.n_obj;
-            for (int sc = 0; sc < scenes_per_tile; ++sc) {
-              const float2 st = stat[sc * 4 + (col >> 6)];
-              float a = st.y * c4.y;
-              float b = fmaf(c4.x - st.x, a, c4.z);
-              const int scene_g = m_idx * scenes_per_tile + sc;
-              if (epi.film.mode == FILM_TIME && scene_g < n_scenes_total) {
-                const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
-                const float s1 = __ldg(fr + n) + 1.0f;
-                b = fmaf(b, s1, __ldg(fr + epi.C + n));
-                a *= s1;
-              }
-              coef[col * scenes_per_tile + sc] = make_float2(a, b);
+        // fold statistics, affine and (per-scene) FiLM into y = v * A + B per (column, scene); v already has the bias
+        {
+          const int col = etid;                      // 256 epilogue threads <-> 256 tile columns
+          const int n = n_idx * BN + col;
+          const float4 c4 = chan[n];
+          const int n_scenes_total = epi.M / epi.n_obj;
+          for (int sc = 0; sc < scenes_per_tile; ++sc) {
+            const float2 st = stat[sc * 4 + (col >> 6)];
+            float a = st.y * c4.y;
+            float b = fmaf(-st.x, a, c4.z);
+            const int scene_g = m_idx * scenes_per_tile + sc;
+            if (epi.film.mode == FILM_TIME && scene_g < n_scenes_total) {
+              const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
+              const float s1 = __ldg(fr + n) + 1.0f;
+              b = fmaf(b, s1, __ldg(fr + epi.C + n));
+              a *= s1;
             }
-          }
-          epi_bar_sync();
-          // ---- pass 2: one FMA + SiLU per element
-          uint32_t ra[32], rb[32];
-          const float2* cb = coef + (hh * HALF) * scenes_per_tile + sc_local;
-          auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
-            if (c + 1 < CHUNKS) load_res(rnext, nbase + (c + 1) * 32);
-            if (row_ok) {
-              float v[32];
-              const float2* cc = cb + c * 32 * scenes_per_tile;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float2 k2 = cc[j * scenes_per_tile];
-                v[j] = silu_tanh(fmaf(__uint_as_float(r[j]), k2.x, k2.y));
-              }
-              store_chunk(v, rcur, nbase + c * 32);
-            }
-          };
-          tmem_ld32_issue(taddr0, ra);
-          tmem_ld_wait();
-          tmem_ld32_issue(taddr0 + 32u, rb);
-          finish(ra, 0, res_a, res_b);
-          tmem_ld_wait();
-          tmem_ld32_issue(taddr0 + 64u, ra);
-          finish(rb, 1, res_b, res_a);
-          tmem_ld_wait();
-          tmem_ld32_issue(taddr0 + 96u, rb);
-          finish(ra, 2, res_a, res_b);
-          tmem_ld_wait();
-          finish(rb, 3, res_b, res_a);
-        } else {
-          // ---- generic pass 2: per-object / per-token FiLM rows (context blocks), or many scenes per tile
-          const float* frow = nullptr;
-          if (row_ok && epi.film.mode != FILM_NONE) {
-            const int scene_g = m_idx * scenes_per_tile + sc_local;
-            if (epi.film.mode == FILM_TIME) frow = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
-            else if (epi.film.mode == FILM_OBJECT) frow = epi.film.base + (int64_t)r_in_scene * epi.film.row_stride;
-            else frow = epi.film.base + (int64_t)m * epi.film.row_stride;
-          }
-#pragma unroll 1
-          for (int c = 0; c < CHUNKS; ++c) {
-            uint32_t r[32];
-            tmem_ld32(taddr0 + uint32_t(c * 32), r);
-            if (row_ok) {
-              const int cl = hh * HALF + c * 32;          // column within the tile
-              const int n0 = n_idx * BN + cl;             // global output column
-              float v[32];
-              const float2 st = stat[sc_local * 4 + (cl >> 6)];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float4 c4 = chan[n0 + j];
-                float y = (__uint_as_float(r[j]) + c4.x - st.x) * st.y;
-                v[j] = fmaf(y, c4.y, c4.z);
-              }
-              if (frow) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
-              if (c > 0) load_res(res_a, n0);
-              store_chunk(v, res_a, n0);
-            }
+            coef[col * scenes_per_tile + sc] = make_float2(a, b);
           }
         }
-      } else {
-        // ---- plain epilogue: bias, activation, residual (TMEM loads software-pipelined)
-        uint32_t ra[32], rb[32];
-        auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
-          if (c + 1 < CHUNKS) load_res(rnext, nbase + (c + 1) * 32);
-          if (row_ok) {
-            const int cl = hh * HALF + c * 32;
-            float v[32];
-            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n_idx * BN + cl);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = b4[j];
-              v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
-              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
-            }
-            if (epi.act == ACT_GELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-            } else if (epi.act == ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
-            }
-            store_chunk(v, rcur, n_idx * BN + cl);
-          }
-        };
-        tmem_ld32_issue(taddr0, ra);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < CHUNKS; c += 2) {
-          if (c + 1 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 1) * 32), rb);
-          finish(ra, c, res_a, res_b);
-          if (c + 1 < CHUNKS) {
-            tmem_ld_wait();
-            if (c + 2 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 2) * 32), ra);
-            finish(rb, c + 1, res_b, res_a);
-            if (c + 2 < CHUNKS) tmem_ld_wait();
-          }
-        }
+        epi_bar_sync();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(ab));
-      if (++ab == 2) { ab = 0; aphase ^= 1u; }
+
+      // ---- pass 2: finish from registers, stage each 32x32 block in swizzled shared memory, TMA-store it
+      const float* frow = nullptr;                  // per-object / per-token FiLM rows (context blocks)
+      if (GN && row_ok && (epi.film.mode == FILM_OBJECT || epi.film.mode == FILM_TOKEN))
+        frow = epi.film.base + (int64_t)(epi.film.mode == FILM_OBJECT ? r_in_scene : m) * epi.film.row_stride;
+      const int rows_q = min(32, max(0, epi.tile_rows - q * 32));          // rows of this quadrant inside the tile
+      const CUtensorMap* dmap = rows_q == 32 ? &tm_d : &tm_dt;
+      const uint32_t stg = base + uint32_t(Cfg::STAGING_OFF) + uint32_t((warp - 2) * 2048);
+      const uint32_t stg_row = stg + uint32_t(lane * 64);
+      const uint32_t swz = uint32_t((lane >> 1) & 3);
+      auto finish = [&](int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
+        if (c + 1 < CHUNKS) load_res(rnext, nbase + (c + 1) * 32);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[c][j]));
+          v[2 * j] = f.x;
+          v[2 * j + 1] = f.y;
+        }
+        if constexpr (GN) {
+          const float2* cc = coef + (hh * HALF + c * 32) * scenes_per_tile + sc_local;
+          if (row_in_tile < epi.tile_rows) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 k2 = cc[j * scenes_per_tile];
+              v[j] = fmaf(v[j], k2.x, k2.y);
+            }
+          }
+          if (frow) {
+            const int n0 = nbase + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
+        }
+        if (epi.res && row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rcur[g]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h2[e]);
+              v[g * 8 + e * 2] += f.x;
+              v[g * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        // the previous TMA store of this warp must have finished READING the staging block
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
+          const uint32_t dst = stg_row + ((uint32_t(g) ^ swz) << 4);       // 64-byte swizzle: chunk ^= (row/2)%4
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                       : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && rows_q > 0 && m0 + q * 32 < epi.M) tma_store_2d(dmap, nbase + c * 32, m0 + q * 32, stg);
+      };
+#pragma unroll
+      for (int c = 0; c < CHUNKS; c += 2) {
+        finish(c, res_a, res_b);
+        if (c + 1 < CHUNKS) finish(c + 1, res_b, res_a);
+      }
     }
+    if (lane == 0) tma_store_wait_all();
     if (epi.trace && warp == 2 && lane == 0) {
       epi.trace[blockIdx.x * 8 + 5] = tw_tf;
       epi.trace[blockIdx.x * 8 + 6] = clock64() - tstart;
@@ -631,6 +611,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 struct TcGemmPlan {
   CUtensorMap tm_a0, tm_a1, tm_w;
+  CUtensorMap tm_d, tm_dt;     // output: 32-row boxes, and the shorter box of the quadrant cut by tile_rows
   TcEpi epi;
   int bn;
   bool gn;
@@ -676,13 +657,14 @@ bool tc_runtime_available(char* err, int err_len) {
 }
 
 static bool encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
-                      uint32_t box_rows, char* err, int err_len) {
+                      uint32_t box_rows, char* err, int err_len, uint32_t box_cols = BK,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {inner, rows};
   cuuint64_t strides[1] = {pitch_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) snprintf(err, err_len, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu pitch=%llu box=%u",
@@ -728,6 +710,17 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   if (const char* e = getenv("DS_TC_CLUSTER")) p->cluster = atoi(e);
   if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) p->cluster = 1;
   if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, p->bn / p->cluster, err, err_len);
+  const int tile_rows = gn ? (BM / g.n_obj) * g.n_obj : BM;
+  if (gn && tile_rows / g.n_obj > TcCfg<256, true>::SPT_FAST) {
+    if (err) snprintf(err, err_len, "fused GroupNorm epilogue supports at most %d scenes per 128-row tile (n_obj=%d)",
+                      TcCfg<256, true>::SPT_FAST, g.n_obj);
+    ok = false;
+  }
+  // output maps: 32 x 32 boxes (64-byte swizzle); the quadrant that the tile boundary cuts uses a shorter box
+  if (ok) ok = encode_2d(&p->tm_d, g.d, g.N, rows_capacity, g.ldd, 32, err, err_len, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  const int tail = tile_rows % 32;
+  if (ok) ok = encode_2d(&p->tm_dt, g.d, g.N, rows_capacity, g.ldd, tail ? tail : 32, err, err_len, 32,
+                         CU_TENSOR_MAP_SWIZZLE_64B);
   if (!ok) {
     delete p;
     return nullptr;
@@ -744,7 +737,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.kb1 = g.k1 / BK;
   p->epi.desc_hi = umma_desc_hi_sw128();
   p->epi.idesc = p->bn == 256 ? TcCfg<256, false>::IDESC : TcCfg<128, false>::IDESC;
-  p->epi.tile_rows = gn ? (BM / g.n_obj) * g.n_obj : BM;
+  p->epi.tile_rows = tile_rows;
   p->epi.n_obj = g.n_obj;
   p->epi.C = g.film_C;
   p->epi.gamma = g.gamma;
@@ -787,7 +780,7 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   }
   const int ncl = total_ct < max_cl ? total_ct : max_cl;
   cfg.gridDim = dim3(ncl * cs);
-  return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, p->tm_d, p->tm_dt, epi, flag_dev);
 }
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {

@@ -279,7 +279,8 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
   b.p = &P;
   b.no_reuse = no_reuse;
   b.C = C;
-  b.fuse = cfg.fuse_level >= 1 && cfg.precision == DS_PREC_BF16 && cfg.gemm_backend != DS_GEMM_SIMT && C % 256 == 0 && C <= 512;
+  b.fuse = cfg.fuse_level >= 1 && cfg.precision == DS_PREC_BF16 && cfg.gemm_backend != DS_GEMM_SIMT && C % 256 == 0 && C <= 512 &&
+           128 / cfg.num_objects <= 10;   // the fused epilogue's coefficient table holds <= 10 scenes per tile
 
   // ---- input + encoder ----
   int xin = b.new_buf(P.kin_pad);
