@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--backend", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="scenes per L2-resident sub-batch (0: whole batch at once)")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device time table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -172,13 +173,13 @@ def main():
         torch.cuda.synchronize(dev)
 
     def resident_step(i):
-        return eng.sample(B, clip_denoised=True, x_init=x_T_dev, seed=100 + i, scene_offset=rank * B)
+        return eng.sample(B, clip_denoised=True, x_init=x_T_dev, seed=100 + i, scene_offset=rank * B, chunk_scenes=args.chunk)
 
     def e2e_step(i):
         # public sampling call with host buffers: H2D of this step's x_T and condition, D2H of the result
         eng.set_context(pos_emb.to(dev, non_blocking=True), shared=True)
         x0 = eng.sample(B, clip_denoised=True, x_init=x_T_host.to(dev, non_blocking=True), seed=100 + i,
-                        scene_offset=rank * B, host_output=True)
+                        scene_offset=rank * B, host_output=True, chunk_scenes=args.chunk)
         return x0
 
     def timed(fn, steps, warmup):

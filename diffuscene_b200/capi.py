@@ -38,7 +38,7 @@ class DsSampleArgs(C.Structure):
         ("x_init_dev", C.c_void_p), ("noise_dev", C.c_void_p), ("partial_dev", C.c_void_p),
         ("num_partial", C.c_int32), ("partial_noise_dev", C.c_void_p), ("traj_freq", C.c_int32),
         ("traj_dev", C.c_void_p), ("use_graph", C.c_int32), ("ddim_times", C.POINTER(C.c_int32)),
-        ("reserved", C.c_int32 * 6)]
+        ("chunk_scenes", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 _lib = None

@@ -704,6 +704,22 @@ extern "C" int ds_sample_loop(ds_handle* h, const ds_sample_args* a, float* out_
   if (h->T == 0) return fail(DS_ERR_STATE, "ds_set_schedule() has not been called");
   CK(cudaSetDevice(h->cfg.device));
   const int B = a->batch;
+  if (a->chunk_scenes > 0 && B > a->chunk_scenes && !a->noise_dev && !a->partial_dev && a->traj_freq <= 0 &&
+      h->ctx_shared && !h->cfg.text_condition) {
+    // sub-batches run the full loop back to back; Philox streams are keyed by the global scene index, so the
+    // result is identical to the unchunked run
+    const size_t per = (size_t)h->cfg.num_objects * h->plan.d;
+    for (int c0 = 0; c0 < B; c0 += a->chunk_scenes) {
+      ds_sample_args sub = *a;
+      sub.batch = std::min(a->chunk_scenes, B - c0);
+      sub.chunk_scenes = 0;
+      sub.scene_offset = a->scene_offset + c0;
+      if (a->x_init_dev) sub.x_init_dev = a->x_init_dev + (size_t)c0 * per;
+      int rc = ds_sample_loop(h, &sub, out_dev + (size_t)c0 * per, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   int rc = ensure_capacity(h, B);
   if (rc) return rc;
   if ((rc = check_ready(h, B))) return rc;

@@ -214,7 +214,7 @@ template <int BN, bool GN>
 struct TcCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = GN ? 3 : ((BN == 256) ? 4 : 6);
+  static constexpr int STAGES = GN ? 3 : ((BN == 256) ? 4 : 6);   // GN: 3 x 48 KB leaves room for its tables
   static constexpr int TMEM_COLS = 2 * BN;                      // two accumulator buffers (256 or 512 columns)
   // epilogue scratch: per-column constants (bias, gamma, beta, -) + GroupNorm partials and statistics
   // per-column constants for ALL N columns of the GEMM, staged once per CTA:
@@ -225,7 +225,7 @@ struct TcCfg {
   static constexpr int SPT_FAST = 10;                    // folded-coefficient fast path: <= 10 scenes per tile
   static constexpr int AB_BYTES = BN * SPT_FAST * 8;     // folded (A, B) coefficients [column][scene]
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 64;   // per epilogue warp: 32 rows x 32 bf16, 64B-swizzled
-  static constexpr int GN_BYTES = GN ? PART_BYTES + 512 + AB_BYTES : 0;
+  static constexpr int GN_BYTES = GN ? PART_BYTES + 512 + 2 * AB_BYTES : 0;   // coefficient table double-buffered
   static constexpr int SCRATCH_OFF = STAGES * STAGE_BYTES + 256;          // barriers occupy the 256 bytes before it
   static constexpr int STAGING_OFF = ((SCRATCH_OFF + CHAN_BYTES + GN_BYTES + 1023) / 1024) * 1024;   // swizzle-atom aligned
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGING_OFF + STAGING_BYTES;
@@ -236,7 +236,7 @@ struct TcCfg {
 };
 
 template <int BN, bool GN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __maxnreg__(200)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
           const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_d,
           const __grid_constant__ CUtensorMap tm_dt, TcEpi epi, int* err_flag) {
@@ -396,11 +396,43 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     }
     epi_bar_sync();
     unsigned long long tw_tf = 0, tstart = clock64(), ntiles = 0;
+    int tile_par = 0;
     for (int tile = cluster_id; tile < total; tile += num_clusters) {
       const int n_idx = tile % num_n, m_idx = (tile / num_n) * int(cs) + int(crank);   // N fastest: neighbours share A in L2
       const int m0 = m_idx * epi.tile_rows;
       const int m = m0 + row_in_tile;
       const bool row_ok = row_in_tile < epi.tile_rows && m < epi.M;
+      float2* const cf = coef + (tile_par ? BN * Cfg::SPT_FAST : 0);   // this tile's coefficient table
+      tile_par ^= 1;
+      if constexpr (GN) {
+        // While the MMAs of this tile are still running: fetch the per-scene FiLM (scale + 1, shift) of this
+        // thread's column for every scene of the tile -- all loads independent, two round trips in total -- and
+        // park them in the (double-buffered) coefficient table, where the same thread folds them in later.
+        const int col = etid, n = n_idx * BN + col;
+        const int n_scenes_total = epi.M / epi.n_obj;
+        if (epi.film.mode == FILM_TIME) {
+          int tt[Cfg::SPT_FAST];
+#pragma unroll
+          for (int sc = 0; sc < Cfg::SPT_FAST; ++sc) {
+            const int scene_g = m_idx * scenes_per_tile + sc;
+            tt[sc] = (sc < scenes_per_tile && scene_g < n_scenes_total) ? __ldg(epi.film.t + scene_g) : -1;
+          }
+          float2 fv[Cfg::SPT_FAST];
+#pragma unroll
+          for (int sc = 0; sc < Cfg::SPT_FAST; ++sc) {
+            fv[sc] = make_float2(1.0f, 0.0f);
+            if (tt[sc] >= 0) {
+              const float* fr = epi.film.base + (int64_t)tt[sc] * epi.film.row_stride;
+              fv[sc] = make_float2(__ldg(fr + n) + 1.0f, __ldg(fr + epi.C + n));
+            }
+          }
+#pragma unroll
+          for (int sc = 0; sc < Cfg::SPT_FAST; ++sc)
+            if (sc < scenes_per_tile) cf[col * scenes_per_tile + sc] = fv[sc];
+        } else {
+          for (int sc = 0; sc < scenes_per_tile; ++sc) cf[col * scenes_per_tile + sc] = make_float2(1.0f, 0.0f);
+        }
+      }
       unsigned long long t0 = epi.trace ? clock64() : 0;
       mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
       if (epi.trace) { tw_tf += clock64() - t0; ++ntiles; }
@@ -500,19 +532,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           const int col = etid;                      // 256 epilogue threads <-> 256 tile columns
           const int n = n_idx * BN + col;
           const float4 c4 = chan[n];
-          const int n_scenes_total = epi.M / epi.n_obj;
           for (int sc = 0; sc < scenes_per_tile; ++sc) {
             const float2 st = stat[sc * 4 + (col >> 6)];
-            float a = st.y * c4.y;
-            float b = fmaf(-st.x, a, c4.z);
-            const int scene_g = m_idx * scenes_per_tile + sc;
-            if (epi.film.mode == FILM_TIME && scene_g < n_scenes_total) {
-              const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride;
-              const float s1 = __ldg(fr + n) + 1.0f;
-              b = fmaf(b, s1, __ldg(fr + epi.C + n));
-              a *= s1;
-            }
-            coef[col * scenes_per_tile + sc] = make_float2(a, b);
+            const float2 f = cf[col * scenes_per_tile + sc];          // (scale + 1, shift) parked at tile start
+            const float a = st.y * c4.y;
+            const float b = fmaf(-st.x, a, c4.z);
+            cf[col * scenes_per_tile + sc] = make_float2(a * f.x, fmaf(b, f.x, f.y));
           }
         }
         epi_bar_sync();
@@ -537,7 +562,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           v[2 * j + 1] = f.y;
         }
         if constexpr (GN) {
-          const float2* cc = coef + (hh * HALF + c * 32) * scenes_per_tile + sc_local;
+          const float2* cc = cf + (hh * HALF + c * 32) * scenes_per_tile + sc_local;
           if (row_in_tile < epi.tile_rows) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {

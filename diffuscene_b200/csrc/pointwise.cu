@@ -261,21 +261,35 @@ __global__ void __launch_bounds__(128) k_linattn(const T* __restrict__ qkv, int 
   const float kinv = 1.0f / ksum;
   for (int r = 0; r < n; ++r) ks[r * 32 + lane] *= kinv;
   __syncwarp();
-  // ctx[d][e] = sum_n k[d,n] v[e,n]; this lane keeps column e = lane
+  // ctx[d][e] = sum_n k[d,n] v[e,n]; this lane keeps column e = lane (k rows read as broadcast float4)
   float ctx[32];
 #pragma unroll
   for (int d = 0; d < 32; ++d) ctx[d] = 0.f;
   for (int r = 0; r < n; ++r) {
-    float v = vs[r * 32 + lane];
+    const float v = vs[r * 32 + lane];
+    const float4* k4 = reinterpret_cast<const float4*>(ks + r * 32);
 #pragma unroll
-    for (int d = 0; d < 32; ++d) ctx[d] += ks[r * 32 + d] * v;
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 kk = k4[d4];
+      ctx[4 * d4] = fmaf(kk.x, v, ctx[4 * d4]);
+      ctx[4 * d4 + 1] = fmaf(kk.y, v, ctx[4 * d4 + 1]);
+      ctx[4 * d4 + 2] = fmaf(kk.z, v, ctx[4 * d4 + 2]);
+      ctx[4 * d4 + 3] = fmaf(kk.w, v, ctx[4 * d4 + 3]);
+    }
   }
   // out[e,n] = sum_d ctx[d][e] q[d,n]
   for (int r = 0; r < n; ++r) {
-    float o = 0.f;
+    const float4* q4 = reinterpret_cast<const float4*>(qs + r * 32);
+    float o0 = 0.f, o1 = 0.f;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o += ctx[d] * qs[r * 32 + d];
-    stf(out + (row0 + r) * ld_out + h * 32 + lane, o);
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 qq = q4[d4];
+      o0 = fmaf(ctx[4 * d4], qq.x, o0);
+      o1 = fmaf(ctx[4 * d4 + 1], qq.y, o1);
+      o0 = fmaf(ctx[4 * d4 + 2], qq.z, o0);
+      o1 = fmaf(ctx[4 * d4 + 3], qq.w, o1);
+    }
+    stf(out + (row0 + r) * ld_out + h * 32 + lane, o0 + o1);
   }
 }
 template <typename T>

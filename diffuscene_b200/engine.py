@@ -141,8 +141,9 @@ class DenoiserEngine:
 
     # ---- sampling -------------------------------------------------------------------------------
     def _sample_args(self, batch, clip_denoised, num_steps, ddim, ddim_eta, seed, scene_offset, x_init, noise,
-                     partial, partial_noise, traj_freq, traj, use_graph, ddim_times):
+                     partial, partial_noise, traj_freq, traj, use_graph, ddim_times, chunk_scenes=0):
         a = capi.DsSampleArgs()
+        a.chunk_scenes = int(chunk_scenes)
         a.batch, a.clip_denoised, a.num_steps = batch, int(clip_denoised), num_steps
         a.ddim, a.ddim_eta, a.seed, a.scene_offset = int(ddim), float(ddim_eta), seed, scene_offset
         a.x_init_dev = None if x_init is None else x_init.data_ptr()
@@ -163,7 +164,7 @@ class DenoiserEngine:
                ddim_eta: float = 0.0, seed: int = 0, scene_offset: int = 0, x_init: Optional[torch.Tensor] = None,
                noise: Optional[torch.Tensor] = None, partial: Optional[torch.Tensor] = None,
                partial_noise: Optional[torch.Tensor] = None, traj_freq: int = 0, use_graph: bool = True,
-               ddim_times: Optional[Sequence[int]] = None, host_output: bool = False):
+               ddim_times: Optional[Sequence[int]] = None, host_output: bool = False, chunk_scenes: int = 0):
         """p_sample_loop (diffusion_ddpm.py:355-371) and its trajectory / completion / DDIM variants.
 
         noise: optional [steps, B, N, d] injected step noise (loop order T-1 .. 0); x_init: optional x_T.
@@ -176,7 +177,7 @@ class DenoiserEngine:
             n_snap = self.lib.ds_traj_count(num_steps if num_steps > 0 else self.num_timesteps, traj_freq)
             traj = torch.empty((n_snap, batch, self.num_objects, self.d), device=dev, dtype=torch.float32)
         a = self._sample_args(batch, clip_denoised, num_steps, ddim, ddim_eta, seed, scene_offset, x_init, noise,
-                              partial, partial_noise, traj_freq, traj, use_graph, ddim_times)
+                              partial, partial_noise, traj_freq, traj, use_graph, ddim_times, chunk_scenes)
         torch.cuda.current_stream(dev).synchronize()
         if host_output:
             out = torch.empty((batch, self.num_objects, self.d), dtype=torch.float32).pin_memory()

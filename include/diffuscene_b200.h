@@ -148,7 +148,9 @@ typedef struct ds_sample_args {
   float* traj_dev;              /* [n_snap, B, N, d] (excluding x_T); n_snap from ds_traj_count      */
   int32_t use_graph;            /* 1: CUDA-graph the step (default); 0: plain launches               */
   const int32_t* ddim_times;    /* optional host array [num_steps+1], descending, last = -1 (:407-409) */
-  int32_t reserved[6];
+  int32_t chunk_scenes;         /* >0: run the whole loop for sub-batches of this many scenes, one after the other,
+                                   so that a sub-batch's activations stay L2-resident (Philox noise path only) */
+  int32_t reserved[5];
 } ds_sample_args;
 DS_API int ds_sample_loop(ds_handle* h, const ds_sample_args* a, float* out_dev, void* stream);
 DS_API int ds_sample_loop_host(ds_handle* h, const ds_sample_args* a, float* out_host);

@@ -110,6 +110,14 @@ def test_batch_independence_at_full_size():
     assert torch.equal(eng.forward(x[perm].contiguous(), t[perm].contiguous()), big[perm])
 
 
+def test_chunked_sampling_is_identical():
+    """Sub-batching (L2-resident chunks run one after the other) must not change any scene's result."""
+    eng, case, spec, inp = get_engine("bed62_loop", "bf16", "tcgen05")
+    a = eng.sample(70, seed=21)
+    b = eng.sample(70, seed=21, chunk_scenes=24)
+    assert torch.equal(a, b)
+
+
 def test_full_sample_smoke_bf16():
     eng, case, spec, inp = get_engine("bed62_loop", "bf16", "tcgen05")
     out = eng.sample(256, seed=11)

@@ -150,3 +150,27 @@ def test_philox_sampling_properties():
     # raw generator moments through a zero-step "loop" is not exposed; check x_T statistics via a 1-step DDIM
     z = eng.sample(64, seed=3, num_steps=1, ddim=True)   # = clamp(x0 estimate): finite and clamped
     assert z.abs().max() <= 1.0 + 1e-6
+
+
+def test_ddim_matches_oracle():
+    """DDIM is a working restatement of the formula at diffusion_ddpm.py:401-444 (dead code in the reference):
+    parity target is the oracle.  eta = 0 (deterministic) and eta = 0.5 with injected noise."""
+    from oracle import diffusion_ref as D
+    from oracle.unet1d_ref import unet1d_forward
+    from diffuscene_b200.weights import seeded_state_dict, unet1d_param_specs
+    eng, case, spec, inp = get_engine("bed62_loop", "fp32")
+    dk = case["diffusion_kwargs"]
+    sched = D.make_schedule(D.make_betas("linear", dk["beta_start"], dk["beta_end"], dk["time_num"]), "v", "fixedsmall")
+    sd = seeded_state_dict(unet1d_param_specs(spec), seed=case["seed"])
+    den = lambda x, t: unet1d_forward(sd, spec, x, t, inp["context"], None)
+    shape = tuple(inp["x"].shape)
+    S = 5
+    times = [tp[0] for tp in D.ddim_times(dk["time_num"], S)] + [-1]
+    for eta in (0.0, 0.5):
+        nz = noise_stream(case["seed"] + 300)
+        ref = D.ddim_sample_loop(sched, den, shape, nz, steps=S, eta=eta)
+        nz = noise_stream(case["seed"] + 300)
+        x_T = nz(shape)
+        noise = torch.stack([nz(shape) if tp[1] >= 0 else torch.zeros(shape) for tp in D.ddim_times(dk["time_num"], S)])
+        out = eng.sample(shape[0], ddim=True, num_steps=S, ddim_eta=eta, x_init=x_T, noise=noise, ddim_times=times)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-3, atol=2e-4)
