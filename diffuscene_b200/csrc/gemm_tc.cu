@@ -236,7 +236,7 @@ struct TcCfg {
 };
 
 template <int BN, bool GN>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
           const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_d,
           const __grid_constant__ CUtensorMap tm_dt, TcEpi epi, int* err_flag) {
