@@ -236,7 +236,8 @@ struct TcCfg {
 };
 
 template <int BN, bool GN>
-__global__ void __maxnreg__(192)
+// 10 warps occupy 12 warp slots of the register file (allocation is per 4 warps): 65536 / (12 * 32) = 170 registers
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
           const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_d,
           const __grid_constant__ CUtensorMap tm_dt, TcEpi epi, int* err_flag) {
@@ -404,6 +405,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       const bool row_ok = row_in_tile < epi.tile_rows && m < epi.M;
       float2* const cf = coef + (tile_par ? BN * Cfg::SPT_FAST : 0);   // this tile's coefficient table
       tile_par ^= 1;
+      if (epi.res && row_ok) {
+        // pull this row's residual segment (HALF bf16 = 1-2 cache lines) towards L2 while the MMAs run
+        const char* rp = reinterpret_cast<const char*>(epi.res + (int64_t)m * epi.ldres + n_idx * BN + hh * HALF);
+#pragma unroll
+        for (int b = 0; b < HALF * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+      }
       if constexpr (GN) {
         // While the MMAs of this tile are still running: fetch the per-scene FiLM (scale + 1, shift) of this
         // thread's column for every scene of the tile -- all loads independent, two round trips in total -- and
