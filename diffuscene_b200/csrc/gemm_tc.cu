@@ -239,8 +239,7 @@ template <int BN, bool GN>
 // 10 warps occupy 12 warp slots of the register file (allocation is per 4 warps): 65536 / (12 * 32) = 170 registers
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
-          const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_d,
-          const __grid_constant__ CUtensorMap tm_dt, TcEpi epi, int* err_flag) {
+          const __grid_constant__ CUtensorMap tm_w, TcEpi epi, int* err_flag) {
   using Cfg = TcCfg<BN, GN>;
   static_assert(!GN || BN == 256, "the GroupNorm epilogue owns 4 groups of 64 channels per tile");
   extern __shared__ uint8_t smem_raw[];
@@ -271,8 +270,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     tma_prefetch_desc(&tm_a0);
     tma_prefetch_desc(&tm_a1);
     tma_prefetch_desc(&tm_w);
-    tma_prefetch_desc(&tm_d);
-    tma_prefetch_desc(&tm_dt);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), cs);       // every CTA of the cluster must have consumed the slot
@@ -447,16 +444,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN + hh * HALF);
 
       const int nbase = n_idx * BN + hh * HALF;     // first global column this warp owns in this tile
-      uint4 res_a[4], res_b[4];
-      auto load_res = [&](uint4 (&rv)[4], int n0) {
-        if (epi.res && row_ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(epi.res + (int64_t)m * epi.ldres + n0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
-        }
-      };
-      load_res(res_a, nbase);                       // chunk 0 residual in flight while the accumulator is read
-
       // ---- pass 1: read the accumulator ONCE (software-pipelined TMEM loads), add the bias, apply the plain
       //      activation or accumulate GroupNorm partial sums, keep the values as packed bf16 in registers, and
       //      hand the TMEM buffer back to the MMA warp before any of the slow work (statistics, stores) starts
@@ -550,17 +537,44 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
         epi_bar_sync();
       }
 
-      // ---- pass 2: finish from registers, stage each 32x32 block in swizzled shared memory, TMA-store it
+      // ---- pass 2: finish from registers.  Global traffic goes through a per-warp 32 x 32 (bf16) staging block in
+      //      shared memory (16-byte pieces XOR-swizzled by (row/2)%4) so that BOTH the residual loads and the output
+      //      stores are coalesced: one warp instruction moves 8 rows x 64 contiguous bytes.
       const float* frow = nullptr;                  // per-object / per-token FiLM rows (context blocks)
       if (GN && row_ok && (epi.film.mode == FILM_OBJECT || epi.film.mode == FILM_TOKEN))
         frow = epi.film.base + (int64_t)(epi.film.mode == FILM_OBJECT ? r_in_scene : m) * epi.film.row_stride;
       const int rows_q = min(32, max(0, epi.tile_rows - q * 32));          // rows of this quadrant inside the tile
-      const CUtensorMap* dmap = rows_q == 32 ? &tm_d : &tm_dt;
       const uint32_t stg = base + uint32_t(Cfg::STAGING_OFF) + uint32_t((warp - 2) * 2048);
-      const uint32_t stg_row = stg + uint32_t(lane * 64);
-      const uint32_t swz = uint32_t((lane >> 1) & 3);
-      auto finish = [&](int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
-        if (c + 1 < CHUNKS) load_res(rnext, nbase + (c + 1) * 32);
+      // row-owner view: lane = row, pieces g = 0..3
+      const uint32_t own_row = stg + uint32_t(lane * 64);
+      const uint32_t own_swz = uint32_t((lane >> 1) & 3);
+      // coalesced view: instruction i covers rows 8i .. 8i+7, lane -> (row 8i + lane/4, piece lane%4)
+      const int co_r = lane >> 2, co_p = lane & 3;
+      const int mrow0 = m0 + q * 32;
+      auto co_addr = [&](int i) {
+        const int r = i * 8 + co_r;
+        return stg + uint32_t(r * 64) + ((uint32_t(co_p) ^ uint32_t((r >> 1) & 3)) << 4);
+      };
+      auto co_ok = [&](int i) { const int r = i * 8 + co_r; return r < rows_q && mrow0 + r < epi.M; };
+      auto sts128 = [](uint32_t a, const uint4& v) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      };
+      auto lds128 = [](uint32_t a) {
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+        return v;
+      };
+      auto finish = [&](int c) {
+        const int n0 = nbase + c * 32;
+        uint4 rg[4];
+        if (epi.res) {                      // coalesced residual fetch, consumed after the math below
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            rg[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (co_ok(i))
+              rg[i] = __ldg(reinterpret_cast<const uint4*>(epi.res + (int64_t)(mrow0 + i * 8 + co_r) * epi.ldres + n0 + co_p * 8));
+          }
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -578,17 +592,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
             }
           }
           if (frow) {
-            const int n0 = nbase + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
         }
-        if (epi.res && row_ok) {
+        if (epi.res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts128(co_addr(i), rg[i]);
+          __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rcur[g]);
+            const uint4 rv = lds128(own_row + ((uint32_t(g) ^ own_swz) << 4));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float2 f = __bfloat1622float2(h2[e]);
@@ -596,31 +613,28 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
               v[g * 8 + e * 2 + 1] += f.y;
             }
           }
+          __syncwarp();
         }
-        // the previous TMA store of this warp must have finished READING the staging block
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 o;
           __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
-          const uint32_t dst = stg_row + ((uint32_t(g) ^ swz) << 4);       // 64-byte swizzle: chunk ^= (row/2)%4
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
-                       : "memory");
+          sts128(own_row + ((uint32_t(g) ^ own_swz) << 4), o);
         }
-        fence_async_smem();
         __syncwarp();
-        if (lane == 0 && rows_q > 0 && m0 + q * 32 < epi.M) tma_store_2d(dmap, nbase + c * 32, m0 + q * 32, stg);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 o = lds128(co_addr(i));
+          if (co_ok(i))
+            *reinterpret_cast<uint4*>(epi.d + (int64_t)(mrow0 + i * 8 + co_r) * epi.ldd + n0 + co_p * 8) = o;
+        }
+        __syncwarp();
       };
 #pragma unroll
-      for (int c = 0; c < CHUNKS; c += 2) {
-        finish(c, res_a, res_b);
-        if (c + 1 < CHUNKS) finish(c + 1, res_b, res_a);
-      }
+      for (int c = 0; c < CHUNKS; ++c) finish(c);
     }
-    if (lane == 0) tma_store_wait_all();
     if (epi.trace && warp == 2 && lane == 0) {
       epi.trace[blockIdx.x * 8 + 5] = tw_tf;
       epi.trace[blockIdx.x * 8 + 6] = clock64() - tstart;
@@ -643,7 +657,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 struct TcGemmPlan {
   CUtensorMap tm_a0, tm_a1, tm_w;
-  CUtensorMap tm_d, tm_dt;     // output: 32-row boxes, and the shorter box of the quadrant cut by tile_rows
   TcEpi epi;
   int bn;
   bool gn;
@@ -748,11 +761,6 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
                       TcCfg<256, true>::SPT_FAST, g.n_obj);
     ok = false;
   }
-  // output maps: 32 x 32 boxes (64-byte swizzle); the quadrant that the tile boundary cuts uses a shorter box
-  if (ok) ok = encode_2d(&p->tm_d, g.d, g.N, rows_capacity, g.ldd, 32, err, err_len, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-  const int tail = tile_rows % 32;
-  if (ok) ok = encode_2d(&p->tm_dt, g.d, g.N, rows_capacity, g.ldd, tail ? tail : 32, err, err_len, 32,
-                         CU_TENSOR_MAP_SWIZZLE_64B);
   if (!ok) {
     delete p;
     return nullptr;
@@ -812,7 +820,7 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   }
   const int ncl = total_ct < max_cl ? total_ct : max_cl;
   cfg.gridDim = dim3(ncl * cs);
-  return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, p->tm_d, p->tm_dt, epi, flag_dev);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
 }
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
