@@ -78,6 +78,7 @@ struct ds_handle {
   int coef_cap = 0;
   StepState* state_dev = nullptr;
   int64_t launches = 0;
+  int t_uniform = 0;          // 1 while every entry of t_dev is the same (inside the sampling loop)
 };
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -117,6 +118,7 @@ static int run_op(ds_handle* h, int idx, int n_scenes, cudaStream_t s) {
       // fallthrough
     case OP_GEMM: {
       if (h->use_tc) {
+        if (o.kind == OP_GEMM_GN) tc_plan_set_uniform_t(h->tc[idx], h->t_uniform);
         int e = launch_gemm_tc(h->tc[idx], M, s);
         if (e) return fail(DS_ERR_CUDA, "tcgen05 GEMM launch '%s' failed: %s", o.name.c_str(),
                            cudaGetErrorString((cudaError_t)e));
@@ -682,6 +684,7 @@ static void model_coefs(ds_handle* h, int t, float* a_x, float* a_o) {
 
 static int step_body(ds_handle* h, const ds_sample_args* a, cudaStream_t s) {
   const Plan& P = h->plan;
+  struct Uni { ds_handle* h; Uni(ds_handle* x) : h(x) { h->t_uniform = 1; } ~Uni() { h->t_uniform = 0; } } uni(h);
   const int B = a->batch, n_obj = h->cfg.num_objects;
   launch_begin_step(h->coef_dev, h->state_dev, h->t_dev, h->x_state, a->partial_dev, a->partial_noise_dev, B, n_obj,
                     P.d, a->partial_dev ? a->num_partial : 0, a->seed, a->scene_offset, s);

@@ -54,6 +54,7 @@ struct TcEpi {
   const float* gamma;
   const float* beta;
   FilmRef film;
+  int film_uniform;      // FILM_TIME only: t[] holds one value for the whole launch (sampling loop)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
 };
 // trace slots: 0 producer wait-empty, 1 producer total, 2 mma wait-tmem-empty, 3 mma wait-full, 4 mma total,
@@ -220,7 +221,8 @@ struct TcCfg {
   // per-column constants for ALL N columns of the GEMM, staged once per CTA:
   //   GN: float4 (bias, gamma, beta, -) for N <= 512;  plain: float bias for N <= 4096
   static constexpr int CHAN_MAX_N = GN ? 512 : 4096;
-  static constexpr int CHAN_BYTES = GN ? CHAN_MAX_N * 16 : CHAN_MAX_N * 4;
+  // GN: bias[N] floats | (gamma, beta)[N] float2 | batch-uniform FiLM (scale+1, shift)[N] float2  = 20 B / column
+  static constexpr int CHAN_BYTES = GN ? CHAN_MAX_N * 20 : CHAN_MAX_N * 4;
   static constexpr int PART_BYTES = GN ? BM * 4 * 8 : 0;
   static constexpr int SPT_FAST = 10;                    // folded-coefficient fast path: <= 10 scenes per tile
   static constexpr int AB_BYTES = BN * SPT_FAST * 8;     // folded (A, B) coefficients [column][scene]
@@ -253,8 +255,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
   uint8_t* const scratch = base_ptr + Cfg::SCRATCH_OFF;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
-  float4* const chan = reinterpret_cast<float4*>(scratch);          // GN: [N] (bias, gamma, beta, 0)
-  float* const bias_s = reinterpret_cast<float*>(scratch);          // plain: [N] bias
+  float* const bias_s = reinterpret_cast<float*>(scratch);          // [N] bias (both epilogues)
+  float2* const gb_s = reinterpret_cast<float2*>(scratch + Cfg::CHAN_MAX_N * 4);     // GN: [N] (gamma, beta)
+  float2* const film_u = reinterpret_cast<float2*>(scratch + Cfg::CHAN_MAX_N * 12);  // GN: [N] uniform-t FiLM
   float2* const part = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES);            // [128 rows][4 groups]
   float2* const stat = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES);   // [scene][4]
   float2* const coef = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512);   // [col][scene]
@@ -385,11 +388,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     const int r_in_scene = GN ? row_in_tile - sc_local * epi.n_obj : 0;
     const int scenes_per_tile = GN ? epi.tile_rows / epi.n_obj : 0;
     // stage the per-column constants once per CTA
+    // film_uniform: every scene of the launch has the same timestep (the sampling loop), so the per-scene FiLM row
+    // is one row for the whole kernel and is staged here instead of being fetched per tile
+    const bool film_uni = GN && epi.film.mode == FILM_TIME && epi.film_uniform;
+    const float* fr_u = film_uni ? epi.film.base + (int64_t)__ldg(epi.film.t) * epi.film.row_stride : nullptr;
     for (int n = etid; n < epi.N; n += EPI_WARPS * 32) {
+      bias_s[n] = epi.bias ? __ldg(epi.bias + n) : 0.f;
       if constexpr (GN) {
-        chan[n] = make_float4(epi.bias ? __ldg(epi.bias + n) : 0.f, __ldg(epi.gamma + n), __ldg(epi.beta + n), 0.f);
-      } else {
-        bias_s[n] = epi.bias ? __ldg(epi.bias + n) : 0.f;
+        gb_s[n] = make_float2(__ldg(epi.gamma + n), __ldg(epi.beta + n));
+        film_u[n] = film_uni ? make_float2(__ldg(fr_u + n) + 1.0f, __ldg(fr_u + epi.C + n)) : make_float2(1.0f, 0.0f);
       }
     }
     epi_bar_sync();
@@ -414,7 +421,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
         // park them in the (double-buffered) coefficient table, where the same thread folds them in later.
         const int col = etid, n = n_idx * BN + col;
         const int n_scenes_total = epi.M / epi.n_obj;
-        if (epi.film.mode == FILM_TIME) {
+        if (epi.film.mode == FILM_TIME && !film_uni) {
           int tt[Cfg::SPT_FAST];
 #pragma unroll
           for (int sc = 0; sc < Cfg::SPT_FAST; ++sc) {
@@ -432,9 +439,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           }
 #pragma unroll
           for (int sc = 0; sc < Cfg::SPT_FAST; ++sc)
-            if (sc < scenes_per_tile) cf[col * scenes_per_tile + sc] = fv[sc];
-        } else {
-          for (int sc = 0; sc < scenes_per_tile; ++sc) cf[col * scenes_per_tile + sc] = make_float2(1.0f, 0.0f);
+            if (sc < scenes_per_tile) cf[col * Cfg::SPT_FAST + sc] = fv[sc];
         }
       }
       unsigned long long t0 = epi.trace ? clock64() : 0;
@@ -444,112 +449,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * BN + hh * HALF);
 
       const int nbase = n_idx * BN + hh * HALF;     // first global column this warp owns in this tile
-      // ---- pass 1: read the accumulator ONCE (software-pipelined TMEM loads), add the bias, apply the plain
-      //      activation or accumulate GroupNorm partial sums, keep the values as packed bf16 in registers, and
-      //      hand the TMEM buffer back to the MMA warp before any of the slow work (statistics, stores) starts
-      uint32_t pk[CHUNKS][16];
-      float gs[2] = {0.f, 0.f}, gss[2] = {0.f, 0.f};
-      {
-        uint32_t ra[32], rb[32];
-        auto take = [&](const uint32_t (&r)[32], int c) {
-          float v[32];
-          if constexpr (GN) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r[j]) + chan[nbase + c * 32 + j].x;
-              gs[c >> 1] += v[j];
-              gss[c >> 1] = fmaf(v[j], v[j], gss[c >> 1]);
-            }
-          } else {
-            const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = b4[j];
-              v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
-              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
-            }
-            if (epi.act == ACT_GELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-            } else if (epi.act == ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            pk[c][j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-        };
-        tmem_ld32_issue(taddr0, ra);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < CHUNKS; c += 2) {
-          if (c + 1 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 1) * 32), rb);
-          take(ra, c);
-          if (c + 1 < CHUNKS) {
-            tmem_ld_wait();
-            if (c + 2 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 2) * 32), ra);
-            take(rb, c + 1);
-            if (c + 2 < CHUNKS) tmem_ld_wait();
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(ab));   // accumulator buffer free: the next tile's MMAs may start
-      if (++ab == 2) { ab = 0; aphase ^= 1u; }
-
-      if constexpr (GN) {
-        part[row_in_tile * 4 + hh * 2] = make_float2(gs[0], gss[0]);
-        part[row_in_tile * 4 + hh * 2 + 1] = make_float2(gs[1], gss[1]);
-        epi_bar_sync();
-        if (etid < scenes_per_tile * 4) {
-          const int sc = etid >> 2, g = etid & 3;
-          float s = 0.f, ss = 0.f;
-          for (int r = 0; r < epi.n_obj; ++r) {
-            float2 p2 = part[(sc * epi.n_obj + r) * 4 + g];
-            s += p2.x;
-            ss += p2.y;
-          }
-          const float inv = 1.0f / float(epi.n_obj * 64);
-          const float mean = s * inv;
-          const float var = fmaxf(ss * inv - mean * mean, 0.f);
-          stat[etid] = make_float2(mean, rsqrtf(var + 1e-5f));
-        }
-        epi_bar_sync();
-        // fold statistics, affine and (per-scene) FiLM into y = v * A + B per (column, scene); v already has the bias
-        {
-          const int col = etid;                      // 256 epilogue threads <-> 256 tile columns
-          const int n = n_idx * BN + col;
-          const float4 c4 = chan[n];
-          for (int sc = 0; sc < scenes_per_tile; ++sc) {
-            const float2 st = stat[sc * 4 + (col >> 6)];
-            const float2 f = cf[col * scenes_per_tile + sc];          // (scale + 1, shift) parked at tile start
-            const float a = st.y * c4.y;
-            const float b = fmaf(-st.x, a, c4.z);
-            cf[col * scenes_per_tile + sc] = make_float2(a * f.x, fmaf(b, f.x, f.y));
-          }
-        }
-        epi_bar_sync();
-      }
-
-      // ---- pass 2: finish from registers.  Global traffic goes through a per-warp 32 x 32 (bf16) staging block in
-      //      shared memory (16-byte pieces XOR-swizzled by (row/2)%4) so that BOTH the residual loads and the output
-      //      stores are coalesced: one warp instruction moves 8 rows x 64 contiguous bytes.
-      const float* frow = nullptr;                  // per-object / per-token FiLM rows (context blocks)
-      if (GN && row_ok && (epi.film.mode == FILM_OBJECT || epi.film.mode == FILM_TOKEN))
-        frow = epi.film.base + (int64_t)(epi.film.mode == FILM_OBJECT ? r_in_scene : m) * epi.film.row_stride;
+      // ---- shared pieces of both epilogues -------------------------------------------------------------------
+      // Global traffic goes through a per-warp 32 x 32 (bf16) staging block in shared memory (16-byte pieces
+      // XOR-swizzled by (row/2)%4) so that BOTH the residual loads and the output stores are coalesced: one warp
+      // instruction moves 8 rows x 64 contiguous bytes.
       const int rows_q = min(32, max(0, epi.tile_rows - q * 32));          // rows of this quadrant inside the tile
       const uint32_t stg = base + uint32_t(Cfg::STAGING_OFF) + uint32_t((warp - 2) * 2048);
-      // row-owner view: lane = row, pieces g = 0..3
-      const uint32_t own_row = stg + uint32_t(lane * 64);
+      const uint32_t own_row = stg + uint32_t(lane * 64);                  // row-owner view: lane = row
       const uint32_t own_swz = uint32_t((lane >> 1) & 3);
-      // coalesced view: instruction i covers rows 8i .. 8i+7, lane -> (row 8i + lane/4, piece lane%4)
-      const int co_r = lane >> 2, co_p = lane & 3;
+      const int co_r = lane >> 2, co_p = lane & 3;                         // coalesced view: (row 8i + lane/4, piece lane%4)
       const int mrow0 = m0 + q * 32;
       auto co_addr = [&](int i) {
         const int r = i * 8 + co_r;
@@ -564,10 +472,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
         return v;
       };
-      auto finish = [&](int c) {
-        const int n0 = nbase + c * 32;
-        uint4 rg[4];
-        if (epi.res) {                      // coalesced residual fetch, consumed after the math below
+      // coalesced residual fetch for chunk c (issued one chunk ahead of its use)
+      auto fetch_res = [&](uint4 (&rg)[4], int c) {
+        if (epi.res) {
+          const int n0 = nbase + c * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             rg[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -575,29 +483,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
               rg[i] = __ldg(reinterpret_cast<const uint4*>(epi.res + (int64_t)(mrow0 + i * 8 + co_r) * epi.ldres + n0 + co_p * 8));
           }
         }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[c][j]));
-          v[2 * j] = f.x;
-          v[2 * j + 1] = f.y;
-        }
-        if constexpr (GN) {
-          const float2* cc = cf + (hh * HALF + c * 32) * scenes_per_tile + sc_local;
-          if (row_in_tile < epi.tile_rows) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float2 k2 = cc[j * scenes_per_tile];
-              v[j] = fmaf(v[j], k2.x, k2.y);
-            }
-          }
-          if (frow) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
-        }
+      };
+      // v (this lane's row, 32 columns of chunk c) += residual; -> bf16 -> coalesced store
+      auto emit = [&](float (&v)[32], const uint4 (&rg)[4], int c) {
+        const int n0 = nbase + c * 32;
         if (epi.res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) sts128(co_addr(i), rg[i]);
@@ -632,8 +521,163 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
         }
         __syncwarp();
       };
+      auto release_tmem = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(ab));   // accumulator buffer free: the next tile's MMAs may start
+        if (++ab == 2) { ab = 0; aphase ^= 1u; }
+      };
+
+      if constexpr (GN) {
+        // ---- pass 1: per-row partial (sum, sum of squares) of the two 64-channel groups this warp owns;
+        //      TMEM loads are software-pipelined (next chunk in flight while this one is reduced)
+        {
+          uint32_t ra[32], rb[32];
+          float s = 0.f, ss = 0.f;
+          auto acc = [&](const uint32_t (&r)[32], int c) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase + c * 32);
 #pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) finish(c);
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              const float v0 = __uint_as_float(r[4 * j]) + bb.x, v1 = __uint_as_float(r[4 * j + 1]) + bb.y;
+              const float v2 = __uint_as_float(r[4 * j + 2]) + bb.z, v3 = __uint_as_float(r[4 * j + 3]) + bb.w;
+              s += (v0 + v1) + (v2 + v3);
+              ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+            }
+          };
+          tmem_ld32_issue(taddr0, ra);
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 32u, rb);
+          acc(ra, 0);
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 64u, ra);
+          acc(rb, 1);
+          part[row_in_tile * 4 + hh * 2] = make_float2(s, ss);
+          s = 0.f; ss = 0.f;
+          tmem_ld_wait();
+          tmem_ld32_issue(taddr0 + 96u, rb);
+          acc(ra, 2);
+          tmem_ld_wait();
+          acc(rb, 3);
+          part[row_in_tile * 4 + hh * 2 + 1] = make_float2(s, ss);
+        }
+        epi_bar_sync();
+        if (etid < scenes_per_tile * 4) {
+          const int sc = etid >> 2, g = etid & 3;
+          float s = 0.f, ss = 0.f;
+          for (int r = 0; r < epi.n_obj; ++r) {
+            float2 p2 = part[(sc * epi.n_obj + r) * 4 + g];
+            s += p2.x;
+            ss += p2.y;
+          }
+          const float inv = 1.0f / float(epi.n_obj * 64);
+          const float mean = s * inv;
+          const float var = fmaxf(ss * inv - mean * mean, 0.f);
+          stat[etid] = make_float2(mean, rsqrtf(var + 1e-5f));
+        }
+        epi_bar_sync();
+        // fold bias, statistics, affine and per-scene FiLM into y = acc * A + B per (column, scene)
+        {
+          const int col = etid;                      // 256 epilogue threads <-> 256 tile columns
+          const int n = n_idx * BN + col;
+          const float2 gb = gb_s[n];
+          const float bias = bias_s[n];
+          const bool per_scene = epi.film.mode == FILM_TIME && !film_uni;
+          const float2 fu = film_u[n];                                // (1, 0) unless the timestep is batch-uniform
+#pragma unroll
+          for (int sc = 0; sc < Cfg::SPT_FAST; ++sc) {
+            if (sc < scenes_per_tile) {
+              const float2 st = stat[sc * 4 + (col >> 6)];
+              const float2 f = per_scene ? cf[col * Cfg::SPT_FAST + sc] : fu;   // per-scene rows parked at tile start
+              const float a = st.y * gb.x;
+              const float b = fmaf(bias - st.x, a, gb.y);
+              cf[col * Cfg::SPT_FAST + sc] = make_float2(a * f.x, fmaf(b, f.x, f.y));
+            }
+          }
+        }
+        epi_bar_sync();
+
+        // ---- pass 2: re-read the accumulator, one FMA + SiLU per element, residual, coalesced store
+        const float* frow = nullptr;                  // per-object / per-token FiLM rows (context blocks)
+        if (row_ok && (epi.film.mode == FILM_OBJECT || epi.film.mode == FILM_TOKEN))
+          frow = epi.film.base + (int64_t)(epi.film.mode == FILM_OBJECT ? r_in_scene : m) * epi.film.row_stride;
+        const float2* cb = cf + (hh * HALF) * Cfg::SPT_FAST + (row_in_tile < epi.tile_rows ? sc_local : 0);
+        uint32_t ra[32], rb[32];
+        uint4 rga[4], rgb[4];
+        auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
+          if (c + 1 < CHUNKS) fetch_res(rnext, c + 1);
+          float v[32];
+          const float2* cc = cb + c * 32 * Cfg::SPT_FAST;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 k2 = cc[j * Cfg::SPT_FAST];
+            v[j] = fmaf(__uint_as_float(r[j]), k2.x, k2.y);
+          }
+          if (frow) {
+            const int n0 = nbase + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
+          emit(v, rcur, c);
+        };
+        fetch_res(rga, 0);
+        tmem_ld32_issue(taddr0, ra);
+        tmem_ld_wait();
+        tmem_ld32_issue(taddr0 + 32u, rb);
+        finish(ra, 0, rga, rgb);
+        tmem_ld_wait();
+        tmem_ld32_issue(taddr0 + 64u, ra);
+        finish(rb, 1, rgb, rga);
+        tmem_ld_wait();
+        tmem_ld32_issue(taddr0 + 96u, rb);
+        finish(ra, 2, rga, rgb);
+        tmem_ld_wait();
+        release_tmem();
+        finish(rb, 3, rgb, rga);
+      } else {
+        // ---- plain epilogue: bias, activation, residual (TMEM loads software-pipelined)
+        uint32_t ra[32], rb[32];
+        uint4 rga[4], rgb[4];
+        auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
+          if (c + 1 < CHUNKS) fetch_res(rnext, c + 1);
+          float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+          }
+          if (epi.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+          } else if (epi.act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
+          }
+          emit(v, rcur, c);
+        };
+        fetch_res(rga, 0);
+        tmem_ld32_issue(taddr0, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < CHUNKS; c += 2) {
+          if (c + 1 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 1) * 32), rb);
+          else release_tmem();
+          finish(ra, c, rga, rgb);
+          if (c + 1 < CHUNKS) {
+            tmem_ld_wait();
+            if (c + 2 < CHUNKS) tmem_ld32_issue(taddr0 + uint32_t((c + 2) * 32), ra);
+            else release_tmem();
+            finish(rb, c + 1, rgb, rga);
+            if (c + 2 < CHUNKS) tmem_ld_wait();
+          }
+        }
+      }
     }
     if (epi.trace && warp == 2 && lane == 0) {
       epi.trace[blockIdx.x * 8 + 5] = tw_tf;
@@ -791,6 +835,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
 void tc_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_plan_set_film(TcGemmPlan* p, const FilmRef& f) { p->epi.film = f; }
 void tc_plan_set_trace(TcGemmPlan* p, unsigned long long* trace) { p->epi.trace = trace; }
+void tc_plan_set_uniform_t(TcGemmPlan* p, int uniform) { p->epi.film_uniform = uniform; }
 
 template <int BN, bool GN>
 static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* flag_dev, cudaStream_t s) {
