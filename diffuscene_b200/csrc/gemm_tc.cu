@@ -227,11 +227,15 @@ struct TcCfg {
   static constexpr int SPT_FAST = 10;                    // folded-coefficient fast path: <= 10 scenes per tile
   static constexpr int AB_BYTES = BN * SPT_FAST * 8;     // folded (A, B) coefficients [column][scene]
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 64;   // per epilogue warp: 32 rows x 32 bf16, 64B-swizzled
-  static constexpr int GN_BYTES = GN ? PART_BYTES + 512 + 2 * AB_BYTES : 0;   // coefficient table double-buffered
+  // second region: coefficient double-buffer (per-scene FiLM prefetch) OR the per-object FiLM table (context blocks)
+  static constexpr int AUX_BYTES = 32000;
+  static constexpr int OBJ_MAX = AUX_BYTES / (BN * 4);   // objects per scene supported by the packed table (31)
+  static constexpr int GN_BYTES = GN ? PART_BYTES + 512 + AB_BYTES + AUX_BYTES : 0;
   static constexpr int SCRATCH_OFF = STAGES * STAGE_BYTES + 256;          // barriers occupy the 256 bytes before it
   static constexpr int STAGING_OFF = ((SCRATCH_OFF + CHAN_BYTES + GN_BYTES + 1023) / 1024) * 1024;   // swizzle-atom aligned
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGING_OFF + STAGING_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+  static_assert(!GN || AUX_BYTES >= AB_BYTES, "aux region doubles as the second coefficient buffer");
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
                                     (uint32_t(BM >> 4) << 24);
@@ -261,8 +265,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   float2* const part = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES);            // [128 rows][4 groups]
   float2* const stat = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES);   // [scene][4]
   float2* const coef = reinterpret_cast<float2*>(scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512);   // [col][scene]
+  uint8_t* const aux = scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512 + (GN ? Cfg::AB_BYTES : 0);
+  uint32_t* const film_o = reinterpret_cast<uint32_t*>(aux);       // [col][obj] packed bf16x2 (scale + 1, shift)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // programmatic dependent launch: let the next kernel's CTAs be scheduled as SMs drain (its prologue overlaps
+  // our tail); our own dependent work starts only after griddepcontrol.wait below
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // thread-block cluster: the CS CTAs of a cluster work on CS consecutive M tiles of the same N tile and share
   // the weight tile -- each CTA loads 1/CS of it and multicasts the slice into every CTA's shared memory
   const uint32_t cs = cluster_nctarank();
@@ -295,6 +304,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   if (cs > 1) cluster_sync_all();        // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above touched no activation memory; from here on we read / write buffers of earlier kernels
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int num_m = (epi.M + epi.tile_rows - 1) / epi.tile_rows;
   const int num_n = epi.N / BN;
@@ -391,6 +402,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     // film_uniform: every scene of the launch has the same timestep (the sampling loop), so the per-scene FiLM row
     // is one row for the whole kernel and is staged here instead of being fetched per tile
     const bool film_uni = GN && epi.film.mode == FILM_TIME && epi.film_uniform;
+    // per-object FiLM (context blocks with a batch-shared condition): constant over tiles -> packed table in smem,
+    // (re)built whenever this CTA moves to another N tile (never, when the grid size is even)
+    const bool film_obj = GN && epi.film.mode == FILM_OBJECT && epi.n_obj <= Cfg::OBJ_MAX;
+    int film_obj_n = -1;
     const float* fr_u = film_uni ? epi.film.base + (int64_t)__ldg(epi.film.t) * epi.film.row_stride : nullptr;
     for (int n = etid; n < epi.N; n += EPI_WARPS * 32) {
       bias_s[n] = epi.bias ? __ldg(epi.bias + n) : 0.f;
@@ -407,13 +422,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       const int m0 = m_idx * epi.tile_rows;
       const int m = m0 + row_in_tile;
       const bool row_ok = row_in_tile < epi.tile_rows && m < epi.M;
-      float2* const cf = coef + (tile_par ? BN * Cfg::SPT_FAST : 0);   // this tile's coefficient table
+      float2* const cf = (tile_par && !film_obj) ? reinterpret_cast<float2*>(aux) : coef;   // this tile's coefficient table
       tile_par ^= 1;
       if (epi.res && row_ok) {
         // pull this row's residual segment (HALF bf16 = 1-2 cache lines) towards L2 while the MMAs run
         const char* rp = reinterpret_cast<const char*>(epi.res + (int64_t)m * epi.ldres + n_idx * BN + hh * HALF);
 #pragma unroll
         for (int b = 0; b < HALF * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+      }
+      if (film_obj && film_obj_n != n_idx) {
+        epi_bar_sync();                          // nobody still reads the previous table
+        for (int i = etid; i < BN * epi.n_obj; i += EPI_WARPS * 32) {
+          const int col = i % BN, ob = i / BN;
+          const float* fr = epi.film.base + (int64_t)ob * epi.film.row_stride + n_idx * BN + col;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(__ldg(fr) + 1.0f, __ldg(fr + epi.C));
+          film_o[col * epi.n_obj + ob] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        film_obj_n = n_idx;                      // visible to the readers after the barriers of the statistics pass
       }
       if constexpr (GN) {
         // While the MMAs of this tile are still running: fetch the per-scene FiLM (scale + 1, shift) of this
@@ -599,8 +624,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 
         // ---- pass 2: re-read the accumulator, one FMA + SiLU per element, residual, coalesced store
         const float* frow = nullptr;                  // per-object / per-token FiLM rows (context blocks)
-        if (row_ok && (epi.film.mode == FILM_OBJECT || epi.film.mode == FILM_TOKEN))
+        if (row_ok && !film_obj && (epi.film.mode == FILM_OBJECT || epi.film.mode == FILM_TOKEN))
           frow = epi.film.base + (int64_t)(epi.film.mode == FILM_OBJECT ? r_in_scene : m) * epi.film.row_stride;
+        const uint32_t* fo = film_o + (hh * HALF) * epi.n_obj + r_in_scene;
         const float2* cb = cf + (hh * HALF) * Cfg::SPT_FAST + (row_in_tile < epi.tile_rows ? sc_local : 0);
         uint32_t ra[32], rb[32];
         uint4 rga[4], rgb[4];
@@ -613,7 +639,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
             const float2 k2 = cc[j * Cfg::SPT_FAST];
             v[j] = fmaf(__uint_as_float(r[j]), k2.x, k2.y);
           }
-          if (frow) {
+          if (film_obj) {
+            const uint32_t* fc = fo + c * 32 * epi.n_obj;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t pkd = fc[j * epi.n_obj];
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pkd));
+              v[j] = fmaf(v[j], f.x, f.y);
+            }
+          } else if (frow) {
             const int n0 = nbase + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
@@ -845,13 +879,20 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TcCfg<BN, GN>::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 0; }
+  if (pdl) {      // may start while the previous kernel in the stream drains (it waits at griddepcontrol.wait)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   if (cs > 1) {
     static int cached[3][5] = {{0}};      // [kernel variant][cluster size]
     const int kv = GN ? 2 : (BN == 256 ? 1 : 0);
