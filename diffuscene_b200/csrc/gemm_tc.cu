@@ -86,8 +86,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = clock64();
+  unsigned int spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > WAIT_TIMEOUT_CYCLES) {     // clock read once per 1024 polls
       if (err_flag) atomicExch(err_flag, code);
       __threadfence_system();
       __trap();
@@ -196,11 +197,12 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // x * sigmoid(x) = h + h * tanh(h), h = x / 2  (one MUFU op; |rel err| ~ 2^-11, below the bf16 output ulp)
-__device__ __forceinline__ float silu_tanh(float x) {
-  float h = 0.5f * x, t;
+__device__ __forceinline__ float silu_from_half(float h) {      // argument is x / 2
+  float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+__device__ __forceinline__ float silu_tanh(float x) { return silu_from_half(0.5f * x); }
 
 // GELU in its tanh form (max |deviation| from the erf form ~3e-4, below the bf16 output ulp for |x| > 0.1):
 // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  -- throughput mode only; the fp32 parity path uses erff
@@ -415,6 +417,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       }
     }
     epi_bar_sync();
+    // Global traffic goes through a per-warp 32 x 32 (bf16) staging block in shared memory (16-byte pieces
+    // XOR-swizzled by (row/2)%4) so that BOTH the residual loads and the output stores are coalesced: one warp
+    // instruction moves 8 rows x 64 contiguous bytes.  Two views of the block:
+    //   row-owner view  lane = row, pieces g = 0..3            (own_a[g])
+    //   coalesced view  instruction i: row 8i + lane/4, piece lane%4   (co_a[i])
+    const uint32_t stg = base + uint32_t(Cfg::STAGING_OFF) + uint32_t((warp - 2) * 2048);
+    const int co_r = lane >> 2, co_p = lane & 3;
+    uint32_t own_a[4], co_a[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      own_a[g] = stg + uint32_t(lane * 64) + ((uint32_t(g) ^ uint32_t((lane >> 1) & 3)) << 4);
+      const int r = g * 8 + co_r;
+      co_a[g] = stg + uint32_t(r * 64) + ((uint32_t(co_p) ^ uint32_t((r >> 1) & 3)) << 4);
+    }
+    const int rows_q = min(32, max(0, epi.tile_rows - q * 32));          // rows of this quadrant inside a tile
+    auto sts128 = [](uint32_t a, const uint4& v) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+    auto lds128 = [](uint32_t a) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+      return v;
+    };
     unsigned long long tw_tf = 0, tstart = clock64(), ntiles = 0;
     int tile_par = 0;
     for (int tile = cluster_id; tile < total; tile += num_clusters) {
@@ -435,7 +460,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
         for (int i = etid; i < BN * epi.n_obj; i += EPI_WARPS * 32) {
           const int col = i % BN, ob = i / BN;
           const float* fr = epi.film.base + (int64_t)ob * epi.film.row_stride + n_idx * BN + col;
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(__ldg(fr) + 1.0f, __ldg(fr + epi.C));
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(0.5f * (__ldg(fr) + 1.0f), 0.5f * __ldg(fr + epi.C));   // halved: see SiLU
           film_o[col * epi.n_obj + ob] = *reinterpret_cast<uint32_t*>(&h2);
         }
         film_obj_n = n_idx;                      // visible to the readers after the barriers of the statistics pass
@@ -475,50 +500,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 
       const int nbase = n_idx * BN + hh * HALF;     // first global column this warp owns in this tile
       // ---- shared pieces of both epilogues -------------------------------------------------------------------
-      // Global traffic goes through a per-warp 32 x 32 (bf16) staging block in shared memory (16-byte pieces
-      // XOR-swizzled by (row/2)%4) so that BOTH the residual loads and the output stores are coalesced: one warp
-      // instruction moves 8 rows x 64 contiguous bytes.
-      const int rows_q = min(32, max(0, epi.tile_rows - q * 32));          // rows of this quadrant inside the tile
-      const uint32_t stg = base + uint32_t(Cfg::STAGING_OFF) + uint32_t((warp - 2) * 2048);
-      const uint32_t own_row = stg + uint32_t(lane * 64);                  // row-owner view: lane = row
-      const uint32_t own_swz = uint32_t((lane >> 1) & 3);
-      const int co_r = lane >> 2, co_p = lane & 3;                         // coalesced view: (row 8i + lane/4, piece lane%4)
-      const int mrow0 = m0 + q * 32;
-      auto co_addr = [&](int i) {
+      // per-tile addresses of the coalesced view (4 instructions x 8 rows): predicate, output / residual pointers
+      bool ok4[4];
+      bf16* dp4[4];
+      const bf16* rp4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + co_r;
-        return stg + uint32_t(r * 64) + ((uint32_t(co_p) ^ uint32_t((r >> 1) & 3)) << 4);
-      };
-      auto co_ok = [&](int i) { const int r = i * 8 + co_r; return r < rows_q && mrow0 + r < epi.M; };
-      auto sts128 = [](uint32_t a, const uint4& v) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-      };
-      auto lds128 = [](uint32_t a) {
-        uint4 v;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-        return v;
-      };
+        ok4[i] = r < rows_q && m0 + q * 32 + r < epi.M;
+        dp4[i] = epi.d + (int64_t)(m0 + q * 32 + r) * epi.ldd + nbase + co_p * 8;
+        rp4[i] = epi.res ? epi.res + (int64_t)(m0 + q * 32 + r) * epi.ldres + nbase + co_p * 8 : nullptr;
+      }
       // coalesced residual fetch for chunk c (issued one chunk ahead of its use)
       auto fetch_res = [&](uint4 (&rg)[4], int c) {
         if (epi.res) {
-          const int n0 = nbase + c * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             rg[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (co_ok(i))
-              rg[i] = __ldg(reinterpret_cast<const uint4*>(epi.res + (int64_t)(mrow0 + i * 8 + co_r) * epi.ldres + n0 + co_p * 8));
+            if (ok4[i]) rg[i] = __ldg(reinterpret_cast<const uint4*>(rp4[i] + c * 32));
           }
         }
       };
       // v (this lane's row, 32 columns of chunk c) += residual; -> bf16 -> coalesced store
       auto emit = [&](float (&v)[32], const uint4 (&rg)[4], int c) {
-        const int n0 = nbase + c * 32;
         if (epi.res) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) sts128(co_addr(i), rg[i]);
+          for (int i = 0; i < 4; ++i) sts128(co_a[i], rg[i]);
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint4 rv = lds128(own_row + ((uint32_t(g) ^ own_swz) << 4));
+            const uint4 rv = lds128(own_a[g]);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -535,14 +546,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
-          sts128(own_row + ((uint32_t(g) ^ own_swz) << 4), o);
+          sts128(own_a[g], o);
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint4 o = lds128(co_addr(i));
-          if (co_ok(i))
-            *reinterpret_cast<uint4*>(epi.d + (int64_t)(mrow0 + i * 8 + co_r) * epi.ldd + n0 + co_p * 8) = o;
+          const uint4 o = lds128(co_a[i]);
+          if (ok4[i]) *reinterpret_cast<uint4*>(dp4[i] + c * 32) = o;
         }
         __syncwarp();
       };
@@ -608,6 +618,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           const float2 gb = gb_s[n];
           const float bias = bias_s[n];
           const bool per_scene = epi.film.mode == FILM_TIME && !film_uni;
+          // with the per-object table the halving lives in that table; the generic per-row path halves at the end
+          const float half_scale = (film_obj || epi.film.mode == FILM_TOKEN || (epi.film.mode == FILM_OBJECT && !film_obj)) ? 1.0f : 0.5f;
           const float2 fu = film_u[n];                                // (1, 0) unless the timestep is batch-uniform
 #pragma unroll
           for (int sc = 0; sc < Cfg::SPT_FAST; ++sc) {
@@ -616,7 +628,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
               const float2 f = per_scene ? cf[col * Cfg::SPT_FAST + sc] : fu;   // per-scene rows parked at tile start
               const float a = st.y * gb.x;
               const float b = fmaf(bias - st.x, a, gb.y);
-              cf[col * Cfg::SPT_FAST + sc] = make_float2(a * f.x, fmaf(b, f.x, f.y));
+              // `half_scale`: the table produces y / 2 directly (SiLU's tanh form wants x / 2)
+              cf[col * Cfg::SPT_FAST + sc] = make_float2(a * f.x * half_scale, fmaf(b, f.x, f.y) * half_scale);
             }
           }
         }
@@ -650,10 +663,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           } else if (frow) {
             const int n0 = nbase + c * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
+            for (int j = 0; j < 32; ++j)
+              v[j] = 0.5f * fmaf(v[j], __ldg(frow + n0 + j) + 1.0f, __ldg(frow + epi.C + n0 + j));
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_tanh(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = silu_from_half(v[j]);
           emit(v, rcur, c);
         };
         fetch_res(rga, 0);
@@ -887,7 +901,7 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 0; }
+  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 1; }   // on by default; DS_TC_PDL=0 disables
   if (pdl) {      // may start while the previous kernel in the stream drains (it waits at griddepcontrol.wait)
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;

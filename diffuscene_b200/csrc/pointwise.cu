@@ -227,54 +227,69 @@ void launch_layernorm(const T* in, int ld_in, T* out, int ld_out, const float* g
 // attention cores: 4 heads x 32 channels, one warp per (scene, head), lane = head channel
 // dynamic smem: 4 warps x 3 x n_obj x 33 floats
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int NMAX>
 __global__ void __launch_bounds__(128) k_linattn(const T* __restrict__ qkv, int ld, T* __restrict__ out, int ld_out,
                                                  int n_scenes, int n) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
   const int scene = blockIdx.x;
-  float* qs = sm + h * 3 * n * 32;
+  float* qs = sm + h * 2 * n * 32;
   float* ks = qs + n * 32;
-  float* vs = ks + n * 32;
   const int64_t row0 = (int64_t)scene * n;
   const float scale = 0.17677669529663687f;   // 32^-0.5
+  // all rows of this (scene, head) are fetched up front: 3*n independent loads in flight per lane
+  float qv[NMAX], kv[NMAX], vv[NMAX];
+#pragma unroll
+  for (int r = 0; r < NMAX; ++r) {
+    if (r < n) {
+      const T* p = qkv + (row0 + r) * ld + h * 32 + lane;
+      qv[r] = ldf(p); kv[r] = ldf(p + 128); vv[r] = ldf(p + 256);
+    } else {
+      qv[r] = 0.f; kv[r] = -INFINITY; vv[r] = 0.f;
+    }
+  }
   // q: softmax over the 32 head channels of each token, then * scale (denoise_net.py:226-229)
-  float kmax = -INFINITY;
-  for (int r = 0; r < n; ++r) {
-    const T* p = qkv + (row0 + r) * ld + h * 32 + lane;
-    float q = ldf(p), k = ldf(p + 128), v = ldf(p + 256);
-    float m = warp_max(q);
-    float e = expf(q - m);
-    float ssum = warp_sum(e);
-    qs[r * 32 + lane] = e / ssum * scale;
-    ks[r * 32 + lane] = k;
-    vs[r * 32 + lane] = v;
-    kmax = fmaxf(kmax, k);
+#pragma unroll
+  for (int r = 0; r < NMAX; ++r) {
+    if (r < n) {
+      float m = warp_max(qv[r]);
+      float e = (sizeof(T) == 4) ? expf(qv[r] - m) : __expf(qv[r] - m);   // exact in the fp32 parity mode
+      float ssum = warp_sum(e);
+      qs[r * 32 + lane] = e / ssum * scale;
+    }
   }
   // k: softmax over tokens for each channel (lane-private column)
+  float kmax = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < NMAX; ++r) kmax = fmaxf(kmax, kv[r]);
   float ksum = 0.f;
-  for (int r = 0; r < n; ++r) {
-    float e = expf(ks[r * 32 + lane] - kmax);
-    ks[r * 32 + lane] = e;
-    ksum += e;
+#pragma unroll
+  for (int r = 0; r < NMAX; ++r) {
+    kv[r] = r < n ? ((sizeof(T) == 4) ? expf(kv[r] - kmax) : __expf(kv[r] - kmax)) : 0.f;
+    ksum += kv[r];
   }
   const float kinv = 1.0f / ksum;
-  for (int r = 0; r < n; ++r) ks[r * 32 + lane] *= kinv;
+#pragma unroll
+  for (int r = 0; r < NMAX; ++r)
+    if (r < n) ks[r * 32 + lane] = kv[r] * kinv;
   __syncwarp();
   // ctx[d][e] = sum_n k[d,n] v[e,n]; this lane keeps column e = lane (k rows read as broadcast float4)
   float ctx[32];
 #pragma unroll
   for (int d = 0; d < 32; ++d) ctx[d] = 0.f;
-  for (int r = 0; r < n; ++r) {
-    const float v = vs[r * 32 + lane];
-    const float4* k4 = reinterpret_cast<const float4*>(ks + r * 32);
 #pragma unroll
-    for (int d4 = 0; d4 < 8; ++d4) {
-      const float4 kk = k4[d4];
-      ctx[4 * d4] = fmaf(kk.x, v, ctx[4 * d4]);
-      ctx[4 * d4 + 1] = fmaf(kk.y, v, ctx[4 * d4 + 1]);
-      ctx[4 * d4 + 2] = fmaf(kk.z, v, ctx[4 * d4 + 2]);
-      ctx[4 * d4 + 3] = fmaf(kk.w, v, ctx[4 * d4 + 3]);
+  for (int r = 0; r < NMAX; ++r) {
+    if (r < n) {
+      const float v = vv[r];
+      const float4* k4 = reinterpret_cast<const float4*>(ks + r * 32);
+#pragma unroll
+      for (int d4 = 0; d4 < 8; ++d4) {
+        const float4 kk = k4[d4];
+        ctx[4 * d4] = fmaf(kk.x, v, ctx[4 * d4]);
+        ctx[4 * d4 + 1] = fmaf(kk.y, v, ctx[4 * d4 + 1]);
+        ctx[4 * d4 + 2] = fmaf(kk.z, v, ctx[4 * d4 + 2]);
+        ctx[4 * d4 + 3] = fmaf(kk.w, v, ctx[4 * d4 + 3]);
+      }
     }
   }
   // out[e,n] = sum_d ctx[d][e] q[d,n]
@@ -294,8 +309,10 @@ __global__ void __launch_bounds__(128) k_linattn(const T* __restrict__ qkv, int 
 }
 template <typename T>
 void launch_linattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int n_obj, cudaStream_t s) {
-  size_t smem = size_t(4) * 3 * n_obj * 32 * sizeof(float);
-  k_linattn<T><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+  size_t smem = size_t(4) * 2 * n_obj * 32 * sizeof(float);
+  if (n_obj <= 16) k_linattn<T, 16><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+  else if (n_obj <= 32) k_linattn<T, 32><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+  else k_linattn<T, 64><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
 }
 
 template <typename T>
@@ -820,8 +837,8 @@ void launch_loss_dict_mean(const float* parts, float* dict9, int B, cudaStream_t
 // raise the dynamic shared-memory limit of the attention cores once, outside any stream capture
 void init_pointwise_attrs() {
   const int lim = 200 * 1024;
-  cudaFuncSetAttribute(k_linattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-  cudaFuncSetAttribute(k_linattn<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_linattn<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_linattn<bf16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
   cudaFuncSetAttribute(k_softattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
   cudaFuncSetAttribute(k_softattn<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
   cudaFuncSetAttribute(k_xattn_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
