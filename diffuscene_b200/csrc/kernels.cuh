@@ -52,8 +52,9 @@ struct StepCoef {
   float q_a, q_b;         // completion re-noising: x[:P] = q_a * partial + q_b * noise2
   int   t;                // timestep fed to the denoiser
 };
-struct StepState {        // device-resident loop state (advanced by the kernels themselves)
+struct StepState {        // device-resident loop state (advanced by the kernels themselves), one per handle
   int step;               // loop iteration index (0 .. n_steps-1)
+  unsigned int done;      // blocks of the running step_update kernel that have finished (last one advances `step`)
 };
 // start of a step: t_dev[b] = coef[step].t ; optional completion re-noise of the first P objects
 void launch_begin_step(const StepCoef* coef, const StepState* st, int* t_dev, float* x, const float* partial,

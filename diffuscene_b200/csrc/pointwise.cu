@@ -544,7 +544,6 @@ void launch_begin_step(const StepCoef* coef, const StepState* st, int* t_dev, fl
 
 // x0 = a_x*x + a_o*out ; clamp ; x' = c_0*x0 + c_x*x + c_z*z   (rounding order of diffusion_ddpm.py:236-240,
 // 294-297, 348-350: every product and sum rounded separately, no FMA contraction)
-__device__ unsigned int g_step_done_blocks = 0;
 template <typename T>
 __global__ void k_step_update(const StepCoef* __restrict__ coef, StepState* st, float* __restrict__ x,
                               const T* __restrict__ model_out, int ld_out, const float* __restrict__ noise, int B,
@@ -587,9 +586,9 @@ __global__ void k_step_update(const StepCoef* __restrict__ coef, StepState* st, 
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    unsigned int done = atomicAdd(&g_step_done_blocks, 1u);
+    unsigned int done = atomicAdd(&st->done, 1u);
     if (done == gridDim.x - 1) {
-      g_step_done_blocks = 0;
+      st->done = 0;
       st->step = step + 1;
       __threadfence();
     }
