@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+T=${1:-r11}
+echo "=== all gpu tests"; timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/${T}_t_all.log
+echo "=== bench 4096"; timeout 900 python bench.py --steps 2 --warmup 1 --batch 4096 --profile-ops > gpurun_out/${T}_bench_4096.json 2> gpurun_out/${T}_bench_4096.err; tail -1 gpurun_out/${T}_bench_4096.json | cut -c1-330; head -1 gpurun_out/${T}_bench_4096.err
+echo "=== ncu launch list + dram bytes"; timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 250 -c 250 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 1 --batch 4096 --timesteps 3 --no-cpu-baseline > gpurun_out/${T}_ncu_bench.log 2>&1
+echo done
