@@ -310,8 +310,156 @@ __global__ void __launch_bounds__(128) k_linattn(const T* __restrict__ qkv, int 
     }
   }
 }
+// ---- tensor-core variant of the linear-attention core (bf16 mode) -------------------------------------------
+// Same math as k_linattn, but the two tiny contractions of each (scene, head)
+//     ctx^T[e][d] = sum_n v[n][e] k~[n][d]          (k~ = softmax of k over the scene's tokens)
+//     out^T[e][n] = sum_d ctx^T[e][d] q~[n][d]      (q~ = softmax of q over the 32 head channels, * 32^-1/2)
+// run on mma.sync.m16n8k16 (bf16 operands, fp32 accumulation): 16 HMMAs instead of ~770 FMAs per lane.  These
+// are 32 x 32 x n problems (n <= 32 tokens), far below the 128-row minimum of tcgen05, hence warp-level MMA.
+// The accumulator fragments of the first product are re-used directly as the A fragments of the second (the
+// C layout of two adjacent n-tiles is the A layout of one k-tile).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h2);
+}
+
+template <int NT>     // tokens padded to NT (16 or 32)
+__global__ void __launch_bounds__(128) k_linattn_mma(const bf16* __restrict__ qkv, int ld, bf16* __restrict__ out,
+                                                     int ld_out, int n_scenes, int n) {
+  constexpr int CS = NT + 8;          // channel-major row stride (bf16 elements): conflict-free fragment loads
+  constexpr int QS = 40;              // token-major row stride of q~ (bf16 elements)
+  constexpr int OS = 33;              // staging row stride of the output (fp32)
+  constexpr int WARP_BYTES = 2 * 32 * CS * 2 + NT * QS * 2 + NT * OS * 4;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int scene = blockIdx.x;
+  unsigned char* wb = smraw + h * WARP_BYTES;
+  bf16* vt = reinterpret_cast<bf16*>(wb);                     // [32 ch][CS]  v transposed
+  bf16* kt = vt + 32 * CS;                                    // [32 ch][CS]  softmax(k) transposed
+  bf16* qs = kt + 32 * CS;                                    // [NT tok][QS] softmax(q) * scale
+  float* os = reinterpret_cast<float*>(qs + NT * QS);         // [NT tok][OS] output staging
+  const int64_t row0 = (int64_t)scene * n;
+  const float scale = 0.17677669529663687f;
+  const int g = lane >> 2, t = lane & 3;
+
+  float qv[NT], kv[NT], vv[NT];
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+    if (r < n) {
+      const bf16* p = qkv + (row0 + r) * ld + h * 32 + lane;
+      qv[r] = __bfloat162float(p[0]); kv[r] = __bfloat162float(p[128]); vv[r] = __bfloat162float(p[256]);
+    } else {
+      qv[r] = 0.f; kv[r] = -INFINITY; vv[r] = 0.f;
+    }
+  }
+  // q~: softmax over the 32 channels (lanes) of each token
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+    float e = 0.f;
+    if (r < n) {
+      float m = warp_max(qv[r]);
+      e = __expf(qv[r] - m);
+      e = e / warp_sum(e) * scale;
+    }
+    qs[r * QS + lane] = __float2bfloat16_rn(e);
+  }
+  // k~: softmax over the tokens, per channel (lane-private); v: as is.  Both stored channel-major.
+  float kmax = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < NT; ++r) kmax = fmaxf(kmax, kv[r]);
+  float ksum = 0.f;
+#pragma unroll
+  for (int r = 0; r < NT; ++r) {
+    kv[r] = r < n ? __expf(kv[r] - kmax) : 0.f;
+    ksum += kv[r];
+  }
+  const float kinv = 1.0f / ksum;
+#pragma unroll
+  for (int r = 0; r < NT; r += 2) {
+    *reinterpret_cast<uint32_t*>(kt + lane * CS + r) = pack_bf16x2(kv[r] * kinv, kv[r + 1] * kinv);
+    *reinterpret_cast<uint32_t*>(vt + lane * CS + r) = pack_bf16x2(vv[r], vv[r + 1]);
+  }
+  __syncwarp();
+
+  // ---- ctx^T = V^T K~ : M = e (2 tiles), N = d (4 tiles), K = tokens (NT / 16 steps)
+  float c[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NT / 16; ++ks) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const bf16* r0 = vt + (16 * mt + g) * CS + 16 * ks + 2 * t;
+      const bf16* r1 = r0 + 8 * CS;
+      a[mt][0] = *reinterpret_cast<const uint32_t*>(r0);
+      a[mt][1] = *reinterpret_cast<const uint32_t*>(r1);
+      a[mt][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+      a[mt][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const bf16* kr = kt + (8 * nt + g) * CS + 16 * ks + 2 * t;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
+      mma_bf16_16816(c[0][nt], a[0], b0, b1);
+      mma_bf16_16816(c[1][nt], a[1], b0, b1);
+    }
+  }
+  // ---- out^T = ctx^T Q~^T : M = e (2 tiles), N = tokens (NT / 8 tiles), K = d (2 steps)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      a[ks][0] = pack_bf16x2(c[mt][2 * ks][0], c[mt][2 * ks][1]);
+      a[ks][1] = pack_bf16x2(c[mt][2 * ks][2], c[mt][2 * ks][3]);
+      a[ks][2] = pack_bf16x2(c[mt][2 * ks + 1][0], c[mt][2 * ks + 1][1]);
+      a[ks][3] = pack_bf16x2(c[mt][2 * ks + 1][2], c[mt][2 * ks + 1][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT / 8; ++nt) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const bf16* qr = qs + (8 * nt + g) * QS + 16 * ks + 2 * t;
+        mma_bf16_16816(o, a[ks], *reinterpret_cast<const uint32_t*>(qr), *reinterpret_cast<const uint32_t*>(qr + 8));
+      }
+      // o[0], o[1]: (e = 16mt + g, tokens 8nt + 2t, +1); o[2], o[3]: e + 8
+      os[(8 * nt + 2 * t) * OS + 16 * mt + g] = o[0];
+      os[(8 * nt + 2 * t + 1) * OS + 16 * mt + g] = o[1];
+      os[(8 * nt + 2 * t) * OS + 16 * mt + g + 8] = o[2];
+      os[(8 * nt + 2 * t + 1) * OS + 16 * mt + g + 8] = o[3];
+    }
+  }
+  __syncwarp();
+  for (int r = 0; r < n; ++r) out[(row0 + r) * ld_out + h * 32 + lane] = __float2bfloat16_rn(os[r * OS + lane]);
+}
+template <int NT> static size_t linattn_mma_smem() {
+  return 4 * size_t(2 * 32 * (NT + 8) * 2 + NT * 40 * 2 + NT * 33 * 4);
+}
+
 template <typename T>
 void launch_linattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int n_obj, cudaStream_t s) {
+  if constexpr (sizeof(T) == 2) {       // bf16 mode: warp-level tensor-core variant
+    if (n_obj <= 16) {
+      k_linattn_mma<16><<<n_scenes, 128, linattn_mma_smem<16>(), s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      return;
+    }
+    if (n_obj <= 32) {
+      k_linattn_mma<32><<<n_scenes, 128, linattn_mma_smem<32>(), s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      return;
+    }
+  }
   size_t smem = size_t(4) * 2 * n_obj * 32 * sizeof(float);
   if (n_obj == 12) k_linattn<T, 12, 12><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
   else if (n_obj == 21) k_linattn<T, 21, 21><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);

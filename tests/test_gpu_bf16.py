@@ -110,6 +110,22 @@ def test_batch_independence_at_full_size():
     assert torch.equal(eng.forward(x[perm].contiguous(), t[perm].contiguous()), big[perm])
 
 
+def test_batch_independence_living_room_shape():
+    """N = 21 objects: 126-row tiles (6 scenes), 21-entry per-object FiLM table, x0-prediction, fixedlarge variance."""
+    eng, case, spec, inp = get_engine("liv65", "bf16", "tcgen05")
+    B = 1500
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(B, case["N"], spec.point_dim, generator=g).cuda()
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    big = eng.forward(x, t)
+    assert torch.isfinite(big).all()
+    small = eng.forward(x[:7].contiguous(), t[:7].contiguous())
+    assert torch.equal(big[:7], small)
+    s1 = eng.sample(40, seed=4, num_steps=6)
+    s2 = eng.sample(13, seed=4, num_steps=6, scene_offset=27)
+    assert torch.equal(s1[27:], s2)            # sharding by scene does not change any scene's sample
+
+
 def test_chunked_sampling_is_identical():
     """Sub-batching (L2-resident chunks run one after the other) must not change any scene's result."""
     eng, case, spec, inp = get_engine("bed62_loop", "bf16", "tcgen05")
