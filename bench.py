@@ -137,6 +137,8 @@ def main():
     ap.add_argument("--backend", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="scenes per L2-resident sub-batch (0: whole batch at once)")
+    ap.add_argument("--fuse", type=int, default=None, help="fuse_level override (1: row-major fused GroupNorm GEMM, "
+                                                            "2: channels-on-lanes variant); default: the engine's")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device time table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -157,7 +159,8 @@ def main():
 
     spec = NetSpec.from_net_kwargs(BED)
     N_OBJ, T, B = 12, args.timesteps, args.batch
-    eng = DenoiserEngine(spec, N_OBJ, T, precision=args.precision, gemm_backend=args.backend, device=local)
+    eng = DenoiserEngine(spec, N_OBJ, T, precision=args.precision, gemm_backend=args.backend, device=local,
+                         fuse_level=args.fuse)
     eng.load_state_dict(seeded_state_dict(unet1d_param_specs(spec), seed=0))      # random-init weights
     eng.set_schedule(make_tables(get_betas("linear", 1e-4, 0.02, T), "v", "fixedsmall"))
     g = torch.Generator().manual_seed(1)

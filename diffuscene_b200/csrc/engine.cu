@@ -43,6 +43,7 @@ struct ds_handle {
   Plan plan;
   bool taps = false;
   bool bf16_mode = false, use_tc = false;
+  bool gnt = false;      // fused GroupNorm convs run the channels-on-lanes kernel (weights stored row-permuted)
   size_t esz = 4;
   cudaStream_t own_stream = nullptr;
   std::map<std::string, std::vector<float>> host_w;
@@ -227,7 +228,7 @@ static int ensure_capacity(ds_handle* h, int n_scenes) {
       GemmArgs g;
       memset(&g, 0, sizeof g);
       if (o.kind == OP_GEMM_GN) {
-        g.gn = 1; g.n_obj = n_obj; g.film_C = P.C;
+        g.gn = h->gnt ? 2 : 1; g.n_obj = n_obj; g.film_C = P.C;
         g.gamma = h->varena + h->v_off[o.gamma];
         g.beta = h->varena + h->v_off[o.beta];
         g.film = film_ref(h, o);
@@ -329,6 +330,9 @@ extern "C" int ds_commit_weights(ds_handle* h) {
   }
   std::vector<char> host(total, 0);
   std::vector<float> mat;
+  std::vector<char> gnt_w(P.wmats.size(), 0);       // weight matrices consumed by fused GroupNorm ops
+  for (const Op& o : P.ops)
+    if (o.kind == OP_GEMM_GN) gnt_w[o.w] = 1;
   for (size_t i = 0; i < P.wmats.size(); ++i) {
     const WRecipe& r = P.wmats[i];
     mat.assign((size_t)r.N * r.K, 0.f);
@@ -352,6 +356,11 @@ extern "C" int ds_commit_weights(ds_handle* h) {
           memcpy(drow, srow, sizeof(float) * pc.cols);
         }
       }
+    }
+    if (h->gnt && gnt_w[i]) {      // row order the channels-on-lanes kernel expects (see tc_gnt_row)
+      std::vector<float> pm(mat.size());
+      for (int rr = 0; rr < r.N; ++rr) memcpy(pm.data() + (size_t)rr * r.K, mat.data() + (size_t)tc_gnt_row(rr) * r.K, sizeof(float) * r.K);
+      mat.swap(pm);
     }
     if (h->bf16_mode) to_bf16_host(mat.data(), (uint16_t*)(host.data() + h->w_off[i]), mat.size());
     else memcpy(host.data() + h->w_off[i], mat.data(), mat.size() * 4);
@@ -469,6 +478,9 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
       return fail(DS_ERR_CUDA, "%s", err);
     }
   }
+  // fuse_level 2: the fused conv + GroupNorm ops use the channels-on-lanes tcgen05 kernel where it applies
+  h->gnt = h->use_tc && cfg->fuse_level >= 2 && tc_gnt_supported(cfg->num_objects, h->plan.C);
+  if (const char* e = getenv("DS_GNT")) h->gnt = h->gnt && atoi(e) != 0;
   cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete h;
@@ -1072,7 +1084,11 @@ extern "C" int ds_test_gemm_trace(const void* a_dev, const void* w_dev, const fl
   memset(&g, 0, sizeof g);
   g.a0 = a_dev; g.lda0 = K; g.k0 = K; g.w = w_dev; g.ldw = K; g.bias = bias_dev; g.d = d_dev; g.ldd = N;
   g.res = res_dev; g.ldres = N; g.M = M; g.N = N;
-  if (n_obj > 0) { g.gn = 1; g.n_obj = n_obj; g.film_C = N; g.gamma = gamma_dev; g.beta = beta_dev; g.film.mode = FILM_NONE; }
+  // n_obj < 0: the channels-on-lanes variant (the caller passes the weight rows in tc_gnt_row order)
+  if (n_obj != 0) {
+    g.gn = n_obj < 0 ? 2 : 1; g.n_obj = n_obj < 0 ? -n_obj : n_obj; g.film_C = N; g.gamma = gamma_dev; g.beta = beta_dev;
+    g.film.mode = FILM_NONE;
+  }
   char err[256] = "";
   TcGemmPlan* p = tc_plan_create(g, M, err, sizeof err);
   if (!p) return fail(DS_ERR_CUDA, "%s", err);

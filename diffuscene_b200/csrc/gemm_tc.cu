@@ -745,6 +745,420 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------
+// GNT: the fused conv + GroupNorm + FiLM + SiLU (+ residual) GEMM with the OUTPUT CHANNELS on the TMEM lanes
+// ------------------------------------------------------------------------------------------------
+// D^T[channel, token] = W[channel, K] * X[token, K]^T : the weight tile (128 channels) is the M operand, a run of
+// whole scenes (SC scenes = TOK tokens) is the N operand.  An epilogue thread therefore owns ONE channel and walks
+// over tokens, which removes everything that made the row-major epilogue expensive:
+//   * bias, gamma, beta and the (batch-uniform) FiLM pair of the channel live in registers -- no per-element
+//     shared-memory coefficient loads, no per-tile coefficient table;
+//   * the conv bias never has to be added per element: the statistics of (acc + b) follow from sum(acc) and
+//     sum(acc^2) of the channel over the 12 tokens of a scene;
+//   * a scene is 12 consecutive TMEM columns, so the normalisation constants are per-(thread, scene) scalars.
+// The price is a transposed store: values are packed as (token j, token j+1) pairs and written with
+// stmatrix.trans into a [token][32 channel] staging block (ldmatrix.trans for the residual), which needs the
+// lanes of a warp to hold the channels in the order 8 (lane % 4) + lane / 4.  The host stores the weight rows of
+// these convs in exactly that order inside every block of 32 (ds_commit_weights), so the shuffle costs nothing.
+// GroupNorm statistics: per-(scene, channel) partials -> shared memory -> 8 threads per (scene, group) reduce.
+template <int NOBJ>
+struct GntCfg {
+  static constexpr int SC = (NOBJ == 12) ? 16 : 256 / NOBJ;   // scenes per tile
+  static constexpr int TOK = SC * NOBJ;                         // tokens per tile (192)
+  static constexpr int UN = (TOK + 15) / 16 * 16;               // UMMA N = TMA box rows of the activation tile
+  static constexpr int EPI_W = 16;                              // epilogue warps: 4 per TMEM lane quadrant
+  static constexpr int NP = EPI_W / 4;                          // each quadrant's warps split the scenes NP ways
+  static constexpr int SPP = SC / NP;                           // scenes per warp and tile
+  static constexpr int THREADS = 64 + EPI_W * 32;
+  static constexpr int B_BYTES = UN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 4;
+  static constexpr int ACC_STRIDE = 256;                        // TMEM columns between the two accumulators
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int CHAN_MAX_N = 512;
+  static constexpr int CHAN_BYTES = CHAN_MAX_N * 20;            // bias | (gamma, beta) | uniform FiLM
+  static constexpr int RED_BYTES = SC * 128 * 8;                // (sum, sum of squares) per (scene, channel)
+  static constexpr int STAT_BYTES = SC * 2 * 8;                 // (mean, rstd) per (scene, group of the tile)
+  static constexpr int STG_ROWS = 16;                           // ldmatrix addresses up to token 15 stay inside the block
+  static constexpr int STG_BYTES = STG_ROWS * 64;               // one [token][32 channel] bf16 block
+  static constexpr int SCRATCH_OFF = STAGES * STAGE_BYTES + 256;
+  static constexpr int RED_OFF = SCRATCH_OFF + CHAN_BYTES;
+  static constexpr int STAT_OFF = RED_OFF + RED_BYTES;
+  static constexpr int STG_OFF = (STAT_OFF + STAT_BYTES + 127) / 128 * 128;
+  static constexpr int SMEM_BYTES = 1024 + STG_OFF + EPI_W * 2 * STG_BYTES;
+  static_assert(SC % NP == 0, "scenes must split evenly over the warps of a quadrant");
+  static_assert(STAGE_BYTES % 1024 == 0, "stages must stay swizzle-atom aligned");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+  static_assert(NOBJ % 2 == 0 && NOBJ == 12, "token pairs must not straddle scenes (only N = 12 is instantiated)");
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(UN >> 3) << 17) |
+                                    (uint32_t(BM >> 4) << 24);
+};
+
+__device__ __forceinline__ void tmem_ld12_issue(uint32_t taddr, uint32_t (&r)[12]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+               : "r"(taddr + 8u)
+               : "memory");
+}
+// wait for the loads above; the registers are listed as read-write so that the compiler cannot move or copy
+// them between the (asynchronous) issue and this point
+__device__ __forceinline__ void tmem_ld12_wait(uint32_t (&r)[12]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void stsm_x4_t(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+               ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void stsm_x2_t(uint32_t addr, uint32_t r0, uint32_t r1) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
+}
+
+template <int NOBJ>
+// 18 warps = 5 on the fullest SM sub-partition: 16384 / (5 * 32) = 102 registers per thread at most
+__global__ void __maxnreg__(96)
+k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x0,
+           const __grid_constant__ CUtensorMap tm_x1, TcEpi epi, int* err_flag) {
+  using Cfg = GntCfg<NOBJ>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
+  float* const bias_s = reinterpret_cast<float*>(base_ptr + Cfg::SCRATCH_OFF);
+  float2* const gb_s = reinterpret_cast<float2*>(base_ptr + Cfg::SCRATCH_OFF + Cfg::CHAN_MAX_N * 4);
+  float2* const film_u = reinterpret_cast<float2*>(base_ptr + Cfg::SCRATCH_OFF + Cfg::CHAN_MAX_N * 12);
+  float2* const red = reinterpret_cast<float2*>(base_ptr + Cfg::RED_OFF);
+  float2* const stat = reinterpret_cast<float2*>(base_ptr + Cfg::STAT_OFF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x0);
+    tma_prefetch_desc(&tm_x1);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), Cfg::EPI_W);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int n_scenes_total = epi.M / NOBJ;
+  const int num_tt = (n_scenes_total + Cfg::SC - 1) / Cfg::SC;     // token tiles
+  const int num_ct = epi.N / BM;                                    // channel tiles
+  const int total = num_tt * num_ct;
+  const int kblocks = epi.kb0 + epi.kb1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      unsigned long long tw = 0, tstart = clock64();
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int ct = tile % num_ct, tt = tile / num_ct;       // channel tiles fastest: neighbours share X in L2
+        const int m0 = tt * Cfg::TOK;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          unsigned long long t0 = epi.trace ? clock64() : 0;
+          mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
+          if (epi.trace) tw += clock64() - t0;
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
+          if (kb < epi.kb0) tma_load_2d(sa + A_BYTES, &tm_x0, kb * BK, m0, full_bar(stage));
+          else tma_load_2d(sa + A_BYTES, &tm_x1, (kb - epi.kb0) * BK, m0, full_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (epi.trace) {
+        epi.trace[blockIdx.x * 8 + 0] = tw;
+        epi.trace[blockIdx.x * 8 + 1] = clock64() - tstart;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int ab = 0;
+      uint32_t aphase = 0;
+      unsigned long long tw_te = 0, tw_f = 0, tstart = clock64();
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        unsigned long long t0 = epi.trace ? clock64() : 0;
+        mbar_wait(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
+        if (epi.trace) tw_te += clock64() - t0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(ab * Cfg::ACC_STRIDE);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          t0 = epi.trace ? clock64() : 0;
+          mbar_wait(full_bar(stage), phase, err_flag, 3);
+          if (epi.trace) tw_f += clock64() - t0;
+          tc_fence_after();
+          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc(sa, epi.desc_hi);                // weights: the M operand
+          const uint64_t bdesc = umma_desc(sa + A_BYTES, epi.desc_hi);      // activations: the N operand
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(ab));
+        if (++ab == 2) { ab = 0; aphase ^= 1u; }
+      }
+      if (epi.trace) {
+        epi.trace[blockIdx.x * 8 + 2] = tw_te;
+        epi.trace[blockIdx.x * 8 + 3] = tw_f;
+        epi.trace[blockIdx.x * 8 + 4] = clock64() - tstart;
+      }
+    }
+  } else {
+    // ---------------- epilogue warps ----------------
+    auto epi_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_W * 32) : "memory"); };
+    const int q = warp & 3;                          // TMEM lane quadrant
+    const int part = (warp - 2) >> 2;                // which scenes of the tile
+    const int etid = threadIdx.x - 64;
+    const int chl = 32 * q + 8 * (lane & 3) + (lane >> 2);      // channel (inside the tile) on this thread's lane
+    const int gq = q >> 1;                                       // GroupNorm group of the tile (64 channels each)
+    const bool film_uni = epi.film.mode == FILM_TIME && epi.film_uniform;
+    const int fmode = epi.film.mode == FILM_OBJECT ? 1 : (epi.film.mode == FILM_TOKEN ? 2 : 0);
+    const bool per_scene_t = epi.film.mode == FILM_TIME && !film_uni;
+    const float* fr_u = film_uni ? epi.film.base + (int64_t)__ldg(epi.film.t) * epi.film.row_stride : nullptr;
+    for (int n = etid; n < epi.N; n += Cfg::EPI_W * 32) {
+      bias_s[n] = epi.bias ? __ldg(epi.bias + n) : 0.f;
+      gb_s[n] = make_float2(__ldg(epi.gamma + n), __ldg(epi.beta + n));
+      film_u[n] = film_uni ? make_float2(__ldg(fr_u + n) + 1.0f, __ldg(fr_u + epi.C + n)) : make_float2(1.0f, 0.0f);
+    }
+    epi_bar();
+    // staging blocks of this warp: [token][32 channels] bf16, 64 B rows
+    const uint32_t stg_in = base + uint32_t(Cfg::STG_OFF) + uint32_t((warp - 2) * 2 * Cfg::STG_BYTES);
+    const uint32_t stg_out = stg_in + uint32_t(Cfg::STG_BYTES);
+    // ldmatrix / stmatrix row address of this lane: matrix lane / 8 holds tokens 2 (lane / 8) + {0, 1}; its row
+    // (lane % 8) = 2 * chunk + e is the 16-byte chunk `chunk` (8 channels) of token 2 (lane / 8) + e
+    const uint32_t mrow = uint32_t((2 * (lane >> 3) + (lane & 1)) * 64 + ((lane & 7) >> 1) * 16);
+    auto sts128 = [](uint32_t a, const uint4& v) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+    auto lds128 = [](uint32_t a) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+      return v;
+    };
+    // coalesced view of a staging block: 16-byte piece `lane` and (for 12 tokens) `lane + 32` of its 48 pieces
+    const int cr0 = lane >> 2, cp0 = lane & 3;
+    int ab = 0;
+    uint32_t aphase = 0;
+    unsigned long long tw_tf = 0, tstart = clock64(), ntiles = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int ct = tile % num_ct, tt = tile / num_ct;
+      const int ch = ct * BM + chl;
+      const float bias = bias_s[ch];
+      const float2 gb = gb_s[ch];
+      const float2 fu = film_u[ch];
+      // scene-constant part of y/2 = (acc + bias - mean) * rstd * P + Q   (modes 1, 2: plain affine, FiLM per element)
+      float P = fmode ? gb.x : 0.5f * gb.x * fu.x;
+      float Q = fmode ? gb.y : 0.5f * fmaf(gb.y, fu.x, fu.y);
+      float Fo[NOBJ], Go[NOBJ];                      // per-object FiLM of this channel (context blocks)
+      if (fmode == 1) {
+#pragma unroll
+        for (int j = 0; j < NOBJ; ++j) {
+          const float* fr = epi.film.base + (int64_t)j * epi.film.row_stride + ch;
+          Fo[j] = 0.5f * (__ldg(fr) + 1.0f);
+          Go[j] = 0.5f * __ldg(fr + epi.C);
+        }
+      }
+      unsigned long long t0 = epi.trace ? clock64() : 0;
+      mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
+      if (epi.trace) { tw_tf += clock64() - t0; ++ntiles; }
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * Cfg::ACC_STRIDE);
+      const int s_begin = part * Cfg::SPP;
+
+      // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
+      {
+        uint32_t va[12];
+        tmem_ld12_issue(taddr + uint32_t(s_begin * NOBJ), va);
+#pragma unroll
+        for (int si = 0; si < Cfg::SPP; ++si) {
+          const int sc = s_begin + si;
+          tmem_ld12_wait(va);
+          float v[NOBJ];
+#pragma unroll
+          for (int j = 0; j < NOBJ; ++j) v[j] = __uint_as_float(va[j]);
+          if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((sc + 1) * NOBJ), va);
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NOBJ; ++j) {
+            s1 += v[j];
+            s2 = fmaf(v[j], v[j], s2);
+          }
+          const float S = fmaf(float(NOBJ), bias, s1);
+          const float SS = fmaf(bias, fmaf(float(NOBJ), bias, 2.0f * s1), s2);
+          red[sc * 128 + 32 * q + lane] = make_float2(S, SS);
+        }
+      }
+      epi_bar();
+      if (etid < Cfg::SC * 2 * 8) {                  // 8 threads per (scene, group): whole warps by construction
+        const int pid = etid >> 3, sub = etid & 7;
+        const float2* rp = red + (pid >> 1) * 128 + (pid & 1) * 64 + sub;
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 p2 = rp[8 * i];
+          s += p2.x;
+          ss += p2.y;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (sub == 0) {
+          const float inv = 1.0f / float(NOBJ * 64);
+          const float mean = s * inv;
+          const float var = fmaxf(ss * inv - mean * mean, 0.f);
+          stat[pid] = make_float2(mean, rsqrtf(var + 1e-5f));
+        }
+      }
+      epi_bar();
+
+      // ---- pass 2: normalise + FiLM + SiLU (+ residual) per scene, transposed store through the staging blocks
+      uint32_t va[12];
+      tmem_ld12_issue(taddr + uint32_t(s_begin * NOBJ), va);
+#pragma unroll 1
+      for (int si = 0; si < Cfg::SPP; ++si) {
+        const int sc = s_begin + si;
+        const int scene_g = tt * Cfg::SC + sc;
+        const bool live = scene_g < n_scenes_total;
+        const int64_t tok0 = (int64_t)scene_g * NOBJ;
+        // residual rows of this warp's 32 channels: coalesced 16-byte pieces, issued before the TMEM wait
+        uint4 rg0 = make_uint4(0u, 0u, 0u, 0u), rg1 = rg0;
+        if (epi.res && live) {
+          const bf16* rb = epi.res + tok0 * epi.ldres + ct * BM + 32 * q;
+          rg0 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)cr0 * epi.ldres + cp0 * 8));
+          if (lane < NOBJ * 4 - 32) rg1 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)(cr0 + 8) * epi.ldres + cp0 * 8));
+        }
+        float Ps = P, Qs = Q;
+        if (per_scene_t && live) {
+          const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride + ch;
+          const float fx = __ldg(fr) + 1.0f, fy = __ldg(fr + epi.C);
+          Ps = 0.5f * gb.x * fx;
+          Qs = 0.5f * fmaf(gb.y, fx, fy);
+        }
+        const float2 st = stat[sc * 2 + gq];
+        const float a = st.y * Ps;
+        const float b = fmaf(bias - st.x, a, Qs);
+        tmem_ld12_wait(va);
+        float y[NOBJ];
+#pragma unroll
+        for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(__uint_as_float(va[j]), a, b);
+        if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((sc + 1) * NOBJ), va);
+        else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(ab));          // accumulator drained: the next tile's MMAs may start
+        }
+        if (fmode == 1) {
+#pragma unroll
+          for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(y[j], Fo[j], Go[j]);
+        } else if (fmode == 2) {
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < NOBJ; ++j) {
+              const float* fr = epi.film.base + (tok0 + j) * epi.film.row_stride + ch;
+              y[j] = 0.5f * fmaf(y[j], __ldg(fr) + 1.0f, __ldg(fr + epi.C));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NOBJ; ++j) y[j] = silu_from_half(y[j]);
+        if (epi.res) {
+          sts128(stg_in + uint32_t(lane * 16), rg0);
+          if (lane < NOBJ * 4 - 32) sts128(stg_in + uint32_t((lane + 32) * 16), rg1);
+          __syncwarp();
+          uint32_t r4[4], r2[2];
+          ldsm_x4_t(r4, stg_in + mrow);
+          ldsm_x2_t(r2, stg_in + 512u + mrow);        // lanes 0-15 address tokens 8..11
+          const uint32_t rr[6] = {r4[0], r4[1], r4[2], r4[3], r2[0], r2[1]};
+#pragma unroll
+          for (int i = 0; i < NOBJ / 2; ++i) {
+            y[2 * i] += __uint_as_float(rr[i] << 16);
+            y[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+          }
+        }
+        uint32_t pk[NOBJ / 2];
+#pragma unroll
+        for (int i = 0; i < NOBJ / 2; ++i) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        stsm_x4_t(stg_out + mrow, pk[0], pk[1], pk[2], pk[3]);
+        stsm_x2_t(stg_out + 512u + mrow, pk[4], pk[5]);
+        __syncwarp();
+        if (live) {
+          bf16* db = epi.d + tok0 * epi.ldd + ct * BM + 32 * q;
+          const uint4 o0 = lds128(stg_out + uint32_t(lane * 16));
+          *reinterpret_cast<uint4*>(db + (int64_t)cr0 * epi.ldd + cp0 * 8) = o0;
+          if (lane < NOBJ * 4 - 32) {
+            const uint4 o1 = lds128(stg_out + uint32_t((lane + 32) * 16));
+            *reinterpret_cast<uint4*>(db + (int64_t)(cr0 + 8) * epi.ldd + cp0 * 8) = o1;
+          }
+        }
+        __syncwarp();
+      }
+      if (++ab == 2) { ab = 0; aphase ^= 1u; }
+    }
+    if (epi.trace && warp == 2 && lane == 0) {
+      epi.trace[blockIdx.x * 8 + 5] = tw_tf;
+      epi.trace[blockIdx.x * 8 + 6] = clock64() - tstart;
+      epi.trace[blockIdx.x * 8 + 7] = ntiles;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
 struct TcGemmPlan {
@@ -752,6 +1166,7 @@ struct TcGemmPlan {
   TcEpi epi;
   int bn;
   bool gn;
+  bool gnt;          // GroupNorm epilogue, channels-on-lanes variant (weights stored in the permuted row order)
   int num_sms;
   int cluster;       // CTAs per cluster (weight-tile multicast width): 1, 2 or 4
   int max_clusters;  // co-resident clusters of that size
@@ -789,6 +1204,7 @@ bool tc_runtime_available(char* err, int err_len) {
   cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
   return true;
 }
@@ -826,6 +1242,11 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     return nullptr;
   }
   const bool gn = g.gn != 0;
+  const bool gnt = g.gn == 2;
+  if (gnt && !tc_gnt_supported(g.n_obj, g.N)) {
+    if (err) snprintf(err, err_len, "channels-on-lanes GroupNorm GEMM needs n_obj == 12 and N %% 128 == 0, N <= 512");
+    return nullptr;
+  }
   if (gn && (g.N % 256 || g.N > TcCfg<256, true>::CHAN_MAX_N || g.n_obj < 1 || g.n_obj > 128 || !g.gamma || !g.beta)) {
     if (err) snprintf(err, err_len, "fused GroupNorm epilogue needs N%%256==0, N<=512, 1<=n_obj<=128, gamma/beta");
     return nullptr;
@@ -839,16 +1260,19 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   // BN = 256 halves the A re-reads; keep 128 when N is not a multiple of 256
   p->bn = (g.N % 256 == 0) ? 256 : 128;
   p->gn = gn;
+  p->gnt = gnt;
   p->num_sms = g_num_sms;
-  bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, BM, err, err_len);
-  if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, BM, err, err_len);
+  const uint32_t act_box = gnt ? uint32_t(GntCfg<12>::UN) : uint32_t(BM);     // rows of one activation tile
+  bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, act_box, err, err_len);
+  if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, act_box, err, err_len);
   if (ok && !g.a1) p->tm_a1 = p->tm_a0;
   p->cluster = 1;
   if (const char* e = getenv("DS_TC_CLUSTER")) p->cluster = atoi(e);
   if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) p->cluster = 1;
-  if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, p->bn / p->cluster, err, err_len);
-  const int tile_rows = gn ? (BM / g.n_obj) * g.n_obj : BM;
-  if (gn && tile_rows / g.n_obj > TcCfg<256, true>::SPT_FAST) {
+  if (gnt) p->cluster = 1;
+  if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, gnt ? BM : p->bn / p->cluster, err, err_len);
+  const int tile_rows = gnt ? GntCfg<12>::TOK : (gn ? (BM / g.n_obj) * g.n_obj : BM);
+  if (gn && !gnt && tile_rows / g.n_obj > TcCfg<256, true>::SPT_FAST) {
     if (err) snprintf(err, err_len, "fused GroupNorm epilogue supports at most %d scenes per 128-row tile (n_obj=%d)",
                       TcCfg<256, true>::SPT_FAST, g.n_obj);
     ok = false;
@@ -923,9 +1347,38 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
 }
 
+bool tc_gnt_supported(int n_obj, int N) { return n_obj == 12 && N % BM == 0 && N <= GntCfg<12>::CHAN_MAX_N; }
+
+static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cudaStream_t s) {
+  using Cfg = GntCfg<12>;
+  const int n_scenes = epi.M / 12;
+  const int total = ((n_scenes + Cfg::SC - 1) / Cfg::SC) * (epi.N / BM);
+  if (total == 0) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cfg.gridDim = dim3(total < p->num_sms ? total : p->num_sms);
+  cudaLaunchAttribute attr[1];
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 1; }
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<12>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
+}
+
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   TcEpi epi = p->epi;
   epi.M = M;
+  if (p->gnt) {
+    int* fd = nullptr;
+    cudaHostGetDevicePointer((void**)&fd, g_err_flag, 0);
+    return launch_gnt(p, epi, fd, s);
+  }
   const int num_m = (M + epi.tile_rows - 1) / epi.tile_rows;
   const int total_ct = ((num_m + p->cluster - 1) / p->cluster) * (epi.N / p->bn);
   if (total_ct == 0) return 0;

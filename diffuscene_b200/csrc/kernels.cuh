@@ -118,5 +118,9 @@ void tc_plan_set_trace(TcGemmPlan* p, unsigned long long* trace);
 void tc_plan_set_uniform_t(TcGemmPlan* p, int uniform);   // all scenes share one timestep (sampling loop)   // [grid][8] cycle counters   // FiLM tables may be (re)allocated after planning
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s);   // returns 0 or cudaError
 bool tc_runtime_available(char* err, int err_len);
+// GemmArgs.gn == 2 selects the channels-on-lanes GroupNorm GEMM: weight rows must be stored permuted inside every
+// block of 32 output channels (stored row 32 b + l holds channel 32 b + 8 (l % 4) + l / 4)
+bool tc_gnt_supported(int n_obj, int N);
+inline int tc_gnt_row(int stored_row) { const int l = stored_row & 31; return (stored_row & ~31) + 8 * (l & 3) + (l >> 2); }
 
 }  // namespace ds

@@ -7,6 +7,7 @@
 // LinearAttention :208-235, Attention :237-259, LinearAttentionCross :261-297) and
 // scene_synthesis/networks/diffusion_ddpm.py (q_sample :276-286, p_sample :339-352, p_losses :520-652).
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace ds {
 
@@ -444,13 +445,189 @@ __global__ void __launch_bounds__(128) k_linattn_mma(const bf16* __restrict__ qk
   __syncwarp();
   for (int r = 0; r < n; ++r) out[(row0 + r) * ld_out + h * 32 + lane] = __float2bfloat16_rn(os[r * OS + lane]);
 }
+// ---- fragment-layout variant (the one the bf16 mode runs) ----------------------------------------------------
+// Same two contractions, arranged so that almost nothing is reshuffled:
+//   * q is loaded from global memory directly in the MMA fragment layout (thread (g, t) of the warp owns tokens
+//     g, g + 8 and the channel pairs 2t + 8j): its channel softmax is 8 local values + a 4-lane butterfly, and the
+//     result is the A operand of   out[n][e] = sum_d q~[n][d] ctx[d][e]   without touching shared memory;
+//   * v is copied token-major (16-byte vectors) into shared memory and read back with ldmatrix.trans as the A
+//     operand of   ctx^T[e][d] = sum_n v[n][e] k~[n][d];  k is soft-maxed over the tokens with one lane per channel,
+//     stored token-major as bf16 and read back with ldmatrix.trans as the B operand;
+//   * the fp32 accumulator fragments of ctx^T are exactly the B fragments of the second product;
+//   * the output fragments (token g, channel pair 2t of each 8-channel block) are stored as packed bf16x2.
+// ~400 instructions per (scene, head) warp instead of ~1400.
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+template <int NT, int NE>     // tokens padded to NT (16 or 32); NE > 0: compile-time scene size
+__global__ void __launch_bounds__(128) k_linattn_frag(const bf16* __restrict__ qkv, int ld, bf16* __restrict__ out,
+                                                      int ld_out, int n_scenes, int n_rt) {
+  constexpr int MT = NT / 16;         // 16-token tiles
+  constexpr int RS = 40;              // shared-memory row stride (bf16): 80 B, conflict-free for ldmatrix
+  const int n = NE > 0 ? NE : n_rt;
+  __shared__ __align__(16) bf16 sm_v[4][NT * RS];
+  __shared__ __align__(16) bf16 sm_k[4][NT * RS];
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int scene = blockIdx.x;
+  const int64_t row0 = (int64_t)scene * n;
+  bf16* vs = sm_v[h];
+  bf16* ks = sm_k[h];
+  const bf16* base = qkv + row0 * ld + h * 32;
+  const float LOG2E = 1.4426950408889634f;
+
+  // ---- v: token-major copy (rows >= n are zero)
+#pragma unroll
+  for (int idx = lane; idx < NT * 4; idx += 32) {
+    const int r = idx >> 2, part = idx & 3;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < n) val = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * ld + 256 + part * 8));
+    *reinterpret_cast<uint4*>(vs + r * RS + part * 8) = val;
+  }
+  // ---- k~: softmax over the tokens, one lane per channel
+  {
+    float kv[NT];
+    float kmax = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      kv[r] = -INFINITY;
+      if (r < n) kv[r] = __bfloat162float(base[(int64_t)r * ld + 128 + lane]);
+      kmax = fmaxf(kmax, kv[r]);
+    }
+    float ksum = 0.f;
+    const float moff = -kmax * LOG2E;
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+      kv[r] = r < n ? fast_exp2(fmaf(kv[r], LOG2E, moff)) : 0.f;
+      ksum += kv[r];
+    }
+    const float kinv = __fdividef(1.0f, ksum);
+#pragma unroll
+    for (int r = 0; r < NT; ++r) ks[r * RS + lane] = __float2bfloat16_rn(kv[r] * kinv);
+  }
+  // ---- q~: loaded in fragment layout; softmax over the 32 channels of a token = 8 local values + the quad
+  uint32_t qa[MT][2][4];              // [token tile][k-step over d][a0..a3]
+#pragma unroll
+  for (int mq = 0; mq < MT; ++mq) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {  // tokens g (a0, a2) and g + 8 (a1, a3)
+      const int tk = 16 * mq + 8 * hf + g;
+      // every lane runs the quad shuffles (tokens >= n read token 0 and are zeroed afterwards)
+      const bool ok = tk < n;
+      const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (int64_t)(ok ? tk : 0) * ld + 2 * t);
+      uint32_t raw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) raw[j] = __ldg(qp + 4 * j);         // channels 8j + 2t, 8j + 2t + 1
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[2 * j] = __uint_as_float(raw[j] << 16);
+        v[2 * j + 1] = __uint_as_float(raw[j] & 0xffff0000u);
+      }
+      float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+      m = quad_max(m);
+      const float moff = -m * LOG2E;
+      float ssum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = fast_exp2(fmaf(v[j], LOG2E, moff));
+        ssum += v[j];
+      }
+      ssum = quad_sum(ssum);
+      const float sc = ok ? __fdividef(0.17677669529663687f, ssum) : 0.f;      // 32^-1/2 / sum
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(v[2 * j] * sc, v[2 * j + 1] * sc);
+      // channel pair j lives in k-step j / 2, register a0/a1 (j even) or a2/a3 (j odd)
+      qa[mq][0][hf] = pk[0];
+      qa[mq][0][2 + hf] = pk[1];
+      qa[mq][1][hf] = pk[2];
+      qa[mq][1][2 + hf] = pk[3];
+    }
+  }
+  __syncwarp();
+
+  // ---- ctx^T[e][d] = sum_tok v[tok][e] k~[tok][d] : M = e (2 tiles), N = d (4 tiles), K = tokens (MT steps)
+  float c[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+  const uint32_t vs_a = (uint32_t)__cvta_generic_to_shared(vs), ks_a = (uint32_t)__cvta_generic_to_shared(ks);
+  const int mi = lane >> 3, mr = lane & 7;          // ldmatrix: this lane addresses row mr of matrix mi
+#pragma unroll
+  for (int kt = 0; kt < MT; ++kt) {
+    uint32_t a[2][4], b[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)    // matrices: (tok lo, e lo), (tok lo, e hi), (tok hi, e lo), (tok hi, e hi)
+      ldsm_x4_trans(a[mt], vs_a + uint32_t(((16 * kt + 8 * (mi >> 1) + mr) * RS + 16 * mt + 8 * (mi & 1)) * 2));
+#pragma unroll
+    for (int np = 0; np < 2; ++np)    // matrices: (d tile 2np, tok lo), (2np, tok hi), (2np + 1, tok lo), (2np + 1, tok hi)
+      ldsm_x4_trans(b[np], ks_a + uint32_t(((16 * kt + 8 * (mi & 1) + mr) * RS + 8 * (2 * np + (mi >> 1))) * 2));
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(c[mt][nt], a[mt], b[nt >> 1][2 * (nt & 1)], b[nt >> 1][2 * (nt & 1) + 1]);
+  }
+  // ---- out[tok][e] = sum_d q~[tok][d] ctx[d][e] : M = tokens (MT tiles), N = e (4 tiles of 8), K = d (2 steps)
+  uint32_t cb[4][2][2];               // [e tile][k-step][b0, b1]
+#pragma unroll
+  for (int eb = 0; eb < 4; ++eb)
+#pragma unroll
+    for (int ks2 = 0; ks2 < 2; ++ks2) {
+      const int i0 = (eb & 1) * 2;
+      cb[eb][ks2][0] = pack_bf16x2(c[eb >> 1][2 * ks2][i0], c[eb >> 1][2 * ks2][i0 + 1]);
+      cb[eb][ks2][1] = pack_bf16x2(c[eb >> 1][2 * ks2 + 1][i0], c[eb >> 1][2 * ks2 + 1][i0 + 1]);
+    }
+#pragma unroll
+  for (int mq = 0; mq < MT; ++mq) {
+#pragma unroll
+    for (int eb = 0; eb < 4; ++eb) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o, qa[mq][0], cb[eb][0][0], cb[eb][0][1]);
+      mma_bf16_16816(o, qa[mq][1], cb[eb][1][0], cb[eb][1][1]);
+      const int tk0 = 16 * mq + g, tk1 = tk0 + 8;
+      bf16* op = out + (row0 + tk0) * ld_out + h * 32 + 8 * eb + 2 * t;
+      if (tk0 < n) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(o[0], o[1]);
+      if (tk1 < n) *reinterpret_cast<uint32_t*>(op + (int64_t)8 * ld_out) = pack_bf16x2(o[2], o[3]);
+    }
+  }
+}
+
 template <int NT> static size_t linattn_mma_smem() {
   return 4 * size_t(2 * 32 * (NT + 8) * 2 + NT * 40 * 2 + NT * 33 * 4);
 }
 
 template <typename T>
 void launch_linattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int n_obj, cudaStream_t s) {
-  if constexpr (sizeof(T) == 2) {       // bf16 mode: warp-level tensor-core variant
+  if constexpr (sizeof(T) == 2) {       // bf16 mode: warp-level tensor-core variants
+    const bool vec_ok = (ld % 8 == 0) && (ld_out % 2 == 0) && ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 4 == 0);
+    static const bool use_frag = !(getenv("DS_LINATTN_FRAG") && atoi(getenv("DS_LINATTN_FRAG")) == 0);
+    if (vec_ok && use_frag && n_obj <= 32) {
+      if (n_obj == 12) k_linattn_frag<16, 12><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj == 21) k_linattn_frag<32, 21><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj <= 16) k_linattn_frag<16, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      else k_linattn_frag<32, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      return;
+    }
     if (n_obj <= 16) {
       k_linattn_mma<16><<<n_scenes, 128, linattn_mma_smem<16>(), s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
       return;
@@ -515,8 +692,133 @@ __global__ void __launch_bounds__(128) k_softattn(const T* __restrict__ qkv, int
     stf(out + (row0 + i) * ld_out + h * 32 + lane, o);
   }
 }
+// ---- tensor-core softmax attention (bf16 mode): S = q k^T on mma.sync with q and k loaded from global memory
+// directly as A / B fragments, row softmax on the accumulator fragments (keys of a query live in one lane quad),
+// O = P v with the probability fragments re-used as the A operand and v read through ldmatrix.trans.
+template <int NT, int NE>
+__global__ void __launch_bounds__(128) k_softattn_frag(const bf16* __restrict__ qkv, int ld, bf16* __restrict__ out,
+                                                       int ld_out, int n_scenes, int n_rt) {
+  constexpr int MT = NT / 16;
+  constexpr int RS = 40;
+  const int n = NE > 0 ? NE : n_rt;
+  __shared__ __align__(16) bf16 sm_v[4][NT * RS];
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t row0 = (int64_t)blockIdx.x * n;
+  bf16* vs = sm_v[h];
+  const bf16* base = qkv + row0 * ld + h * 32;
+#pragma unroll
+  for (int idx = lane; idx < NT * 4; idx += 32) {
+    const int r = idx >> 2, part = idx & 3;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < n) val = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * ld + 256 + part * 8));
+    *reinterpret_cast<uint4*>(vs + r * RS + part * 8) = val;
+  }
+  // q (A operand: rows = query tokens) and k (B operand: columns = key tokens), both K = d in pairs 8j + 2t
+  uint32_t qa[MT][2][4], kb[2 * MT][2][2];
+#pragma unroll
+  for (int tt = 0; tt < 2 * MT; ++tt) {           // token 8 tt + g
+    const int tk = 8 * tt + g;
+    uint32_t rq[4] = {0u, 0u, 0u, 0u}, rk[4] = {0u, 0u, 0u, 0u};
+    if (tk < n) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(base + (int64_t)tk * ld + 2 * t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rq[j] = __ldg(p + 4 * j);
+        rk[j] = __ldg(p + 64 + 4 * j);              // k block: + 128 channels
+      }
+    }
+    qa[tt >> 1][0][tt & 1] = rq[0];
+    qa[tt >> 1][0][2 + (tt & 1)] = rq[1];
+    qa[tt >> 1][1][tt & 1] = rq[2];
+    qa[tt >> 1][1][2 + (tt & 1)] = rq[3];
+    kb[tt][0][0] = rk[0];
+    kb[tt][0][1] = rk[1];
+    kb[tt][1][0] = rk[2];
+    kb[tt][1][1] = rk[3];
+  }
+  __syncwarp();
+  const uint32_t vs_a = (uint32_t)__cvta_generic_to_shared(vs);
+  const int mi = lane >> 3, mr = lane & 7;
+  const float SCL = 0.17677669529663687f * 1.4426950408889634f;       // 32^-1/2 * log2(e)
+#pragma unroll
+  for (int mq = 0; mq < MT; ++mq) {
+    float sc[2 * MT][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * MT; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      mma_bf16_16816(sc[nt], qa[mq][0], kb[nt][0][0], kb[nt][0][1]);
+      mma_bf16_16816(sc[nt], qa[mq][1], kb[nt][1][0], kb[nt][1][1]);
+    }
+    // rows g (values 0, 1) and g + 8 (values 2, 3); keys 8 nt + 2 t + {0, 1}
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = 8 * nt + 2 * t + e < n;
+        sc[nt][e] = ok ? sc[nt][e] * SCL : -INFINITY;
+        sc[nt][2 + e] = ok ? sc[nt][2 + e] * SCL : -INFINITY;
+        m0 = fmaxf(m0, sc[nt][e]);
+        m1 = fmaxf(m1, sc[nt][2 + e]);
+      }
+    m0 = quad_max(m0);
+    m1 = quad_max(m1);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[nt][e] = fast_exp2(sc[nt][e] - m0);
+        sc[nt][2 + e] = fast_exp2(sc[nt][2 + e] - m1);
+        s0 += sc[nt][e];
+        s1 += sc[nt][2 + e];
+      }
+    const float i0 = __fdividef(1.0f, quad_sum(s0)), i1 = __fdividef(1.0f, quad_sum(s1));
+    uint32_t pa[MT][4];
+#pragma unroll
+    for (int kt = 0; kt < MT; ++kt) {
+      pa[kt][0] = pack_bf16x2(sc[2 * kt][0] * i0, sc[2 * kt][1] * i0);
+      pa[kt][1] = pack_bf16x2(sc[2 * kt][2] * i1, sc[2 * kt][3] * i1);
+      pa[kt][2] = pack_bf16x2(sc[2 * kt + 1][0] * i0, sc[2 * kt + 1][1] * i0);
+      pa[kt][3] = pack_bf16x2(sc[2 * kt + 1][2] * i1, sc[2 * kt + 1][3] * i1);
+    }
+    float o[4][4];
+#pragma unroll
+    for (int eb = 0; eb < 4; ++eb) o[eb][0] = o[eb][1] = o[eb][2] = o[eb][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < MT; ++kt) {
+#pragma unroll
+      for (int ep = 0; ep < 2; ++ep) {            // matrices: (e tile 2ep, tok lo), (2ep, tok hi), (2ep + 1, lo), (2ep + 1, hi)
+        uint32_t b[4];
+        ldsm_x4_trans(b, vs_a + uint32_t(((16 * kt + 8 * (mi & 1) + mr) * RS + 8 * (2 * ep + (mi >> 1))) * 2));
+        mma_bf16_16816(o[2 * ep], pa[kt], b[0], b[1]);
+        mma_bf16_16816(o[2 * ep + 1], pa[kt], b[2], b[3]);
+      }
+    }
+    const int tk0 = 16 * mq + g, tk1 = tk0 + 8;
+#pragma unroll
+    for (int eb = 0; eb < 4; ++eb) {
+      bf16* op = out + (row0 + tk0) * ld_out + h * 32 + 8 * eb + 2 * t;
+      if (tk0 < n) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(o[eb][0], o[eb][1]);
+      if (tk1 < n) *reinterpret_cast<uint32_t*>(op + (int64_t)8 * ld_out) = pack_bf16x2(o[eb][2], o[eb][3]);
+    }
+  }
+}
+
 template <typename T>
 void launch_softattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int n_obj, cudaStream_t s) {
+  if constexpr (sizeof(T) == 2) {
+    const bool vec_ok = (ld % 8 == 0) && (ld_out % 2 == 0) && ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 4 == 0);
+    static const bool use_frag = !(getenv("DS_SOFTATTN_FRAG") && atoi(getenv("DS_SOFTATTN_FRAG")) == 0);
+    if (vec_ok && use_frag && n_obj <= 32) {
+      if (n_obj == 12) k_softattn_frag<16, 12><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj == 21) k_softattn_frag<32, 21><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj <= 16) k_softattn_frag<16, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      else k_softattn_frag<32, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      return;
+    }
+  }
   size_t smem = size_t(4) * 3 * n_obj * 33 * sizeof(float);
   k_softattn<T><<<n_scenes, 128, smem, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
 }

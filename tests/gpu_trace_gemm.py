@@ -13,23 +13,55 @@ lib = capi.load()
 names = ["prod_wait_empty", "prod_total", "mma_wait_tmem", "mma_wait_full", "mma_total", "epi_wait_tfull", "epi_total", "tiles"]
 
 
-def run(M, N, K, n_obj=0, res=False, tag=""):
+def gnt_rows(N):
+    """stored row -> channel of the channels-on-lanes kernel (tc_gnt_row in kernels.cuh)"""
+    r = torch.arange(N)
+    l = r & 31
+    return (r & ~31) + 8 * (l & 3) + (l >> 2)
+
+
+def reference(a, w, bias, gamma, beta, r, n_obj):
+    y = a.float() @ w.float().t() + bias
+    if n_obj:
+        M, N = y.shape
+        z = y.view(M // n_obj, n_obj, N // 64, 64)
+        mean = z.mean(dim=(1, 3), keepdim=True)
+        var = z.var(dim=(1, 3), unbiased=False, keepdim=True)
+        y = ((z - mean) * torch.rsqrt(var + 1e-5)).view(M, N) * gamma + beta
+        y = torch.nn.functional.silu(y)
+    if r is not None:
+        y = y + r.float()
+    return y
+
+
+def run(M, N, K, n_obj=0, res=False, tag="", gnt=False, check=False):
     g = torch.Generator().manual_seed(0)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
     bias = torch.randn(N, generator=g).cuda()
-    gamma = torch.ones(N).cuda()
-    beta = torch.zeros(N).cuda()
+    gamma = (1.0 + 0.2 * torch.randn(N, generator=g)).cuda() if check else torch.ones(N).cuda()
+    beta = (0.2 * torch.randn(N, generator=g)).cuda() if check else torch.zeros(N).cuda()
     r = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda() if res else None
-    d = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    d = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
     tr = np.zeros((256, 8), dtype=np.uint64)
     us = C.c_float()
-    rc = lib.ds_test_gemm_trace(a.data_ptr(), w.data_ptr(), bias.data_ptr(), None if r is None else r.data_ptr(),
-                                d.data_ptr(), M, N, K, n_obj, gamma.data_ptr(), beta.data_ptr(), 20,
+    w_dev = w[gnt_rows(N).cuda()].contiguous() if gnt else w
+    rc = lib.ds_test_gemm_trace(a.data_ptr(), w_dev.data_ptr(), bias.data_ptr(), None if r is None else r.data_ptr(),
+                                d.data_ptr(), M, N, K, -n_obj if gnt else n_obj, gamma.data_ptr(), beta.data_ptr(), 20,
                                 tr.ctypes.data, C.byref(us))
     if rc:
         print("FAILED", lib.ds_last_error().decode())
         return
+    if check:
+        ref = reference(a, w, bias, gamma, beta, r, n_obj)
+        err = (d.float() - ref).abs()
+        bad = (err > 0.05 + 0.02 * ref.abs()).sum().item()
+        print("   check %-20s max|err|=%.4f mean|err|=%.5f  out-of-tolerance=%d  %s" % (
+            tag, err.max().item(), err.mean().item(), bad, "OK" if bad == 0 else "MISMATCH"))
+        if bad:
+            idx = (err > 0.05 + 0.02 * ref.abs()).nonzero()[:8]
+            for i, j in idx.tolist():
+                print("      row %d col %d got %.4f want %.4f" % (i, j, d[i, j].item(), ref[i, j].item()))
     t = tr[:148].astype(np.float64)
     tf = 2.0 * M * N * K / us.value / 1e6
     print("%-28s M=%d N=%d K=%d n_obj=%d res=%d: %.1f us  %.0f TFLOP/s" % (tag, M, N, K, n_obj, res, us.value, tf))
@@ -39,11 +71,31 @@ def run(M, N, K, n_obj=0, res=False, tag=""):
 cl = os.environ.get("DS_TC_CLUSTER", "1")
 print("cluster size", cl)
 M = 49152
+if os.environ.get("GNT_ONLY"):
+    for m_chk in (12 * 16 * 3, 12 * 1000):      # whole tiles / ragged last tile
+        run(m_chk, 512, 512, n_obj=12, tag="GN", check=True)
+        run(m_chk, 512, 512, n_obj=12, tag="GNT", gnt=True, check=True)
+        run(m_chk, 512, 512, n_obj=12, res=True, tag="GNT+res", gnt=True, check=True)
+        run(m_chk, 512, 1024, n_obj=12, res=True, tag="GNT+res K=1024", gnt=True, check=True)
+    run(M, 512, 512, n_obj=12, tag="GNT", gnt=True)
+    run(M, 512, 512, n_obj=12, res=True, tag="GNT+res", gnt=True)
+    run(M, 512, 1024, n_obj=12, res=True, tag="GNT+res K=1024", gnt=True)
+    run(M, 512, 512, n_obj=12, tag="GN")
+    run(M, 512, 512, n_obj=12, res=True, tag="GN+res")
+    sys.exit(0)
 run(M, 512, 512, tag="plain 512x512")
 run(M, 512, 1024, tag="plain 512x1024")
 run(M, 512, 512, res=True, tag="plain+res")
 run(M, 3072, 512, tag="dec.l0")
 run(M, 1024, 512, tag="enc.l1")
+for m_chk in (12 * 16 * 3, 12 * 1000):      # whole tiles / ragged last tile
+    run(m_chk, 512, 512, n_obj=12, tag="GN", check=True)
+    run(m_chk, 512, 512, n_obj=12, tag="GNT", gnt=True, check=True)
+    run(m_chk, 512, 512, n_obj=12, res=True, tag="GNT+res", gnt=True, check=True)
+    run(m_chk, 512, 1024, n_obj=12, res=True, tag="GNT+res K=1024", gnt=True, check=True)
+run(M, 512, 512, n_obj=12, tag="GNT", gnt=True)
+run(M, 512, 512, n_obj=12, res=True, tag="GNT+res", gnt=True)
+run(M, 512, 1024, n_obj=12, res=True, tag="GNT+res K=1024", gnt=True)
 run(M, 512, 512, n_obj=12, tag="GN")
 run(M, 512, 512, n_obj=12, res=True, tag="GN+res")
 run(M, 512, 1024, n_obj=12, res=True, tag="GN+res K=1024")
