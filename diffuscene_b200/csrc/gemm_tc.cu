@@ -1001,12 +1001,24 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           Go[j] = 0.5f * __ldg(fr + epi.C);
         }
       }
+      const int s_begin = part * Cfg::SPP;
+      // residual rows of this warp's 32 channels for one scene: 48 coalesced 16-byte pieces (lane, lane + 32).
+      // Software-pipelined one scene ahead; the first fetch is issued before the accumulator is even complete.
+      uint4 rg0 = make_uint4(0u, 0u, 0u, 0u), rg1 = rg0;
+      auto fetch_res = [&](int sc) {
+        const int scene_g = tt * Cfg::SC + sc;
+        if (scene_g < n_scenes_total) {
+          const bf16* rb = epi.res + (int64_t)scene_g * NOBJ * epi.ldres + ct * BM + 32 * q;
+          rg0 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)cr0 * epi.ldres + cp0 * 8));
+          if (lane < NOBJ * 4 - 32) rg1 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)(cr0 + 8) * epi.ldres + cp0 * 8));
+        }
+      };
+      if (epi.res) fetch_res(s_begin);
       unsigned long long t0 = epi.trace ? clock64() : 0;
       mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
       if (epi.trace) { tw_tf += clock64() - t0; ++ntiles; }
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * Cfg::ACC_STRIDE);
-      const int s_begin = part * Cfg::SPP;
 
       // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
       {
@@ -1065,13 +1077,6 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         const int scene_g = tt * Cfg::SC + sc;
         const bool live = scene_g < n_scenes_total;
         const int64_t tok0 = (int64_t)scene_g * NOBJ;
-        // residual rows of this warp's 32 channels: coalesced 16-byte pieces, issued before the TMEM wait
-        uint4 rg0 = make_uint4(0u, 0u, 0u, 0u), rg1 = rg0;
-        if (epi.res && live) {
-          const bf16* rb = epi.res + tok0 * epi.ldres + ct * BM + 32 * q;
-          rg0 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)cr0 * epi.ldres + cp0 * 8));
-          if (lane < NOBJ * 4 - 32) rg1 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)(cr0 + 8) * epi.ldres + cp0 * 8));
-        }
         float Ps = P, Qs = Q;
         if (per_scene_t && live) {
           const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride + ch;
@@ -1109,6 +1114,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         if (epi.res) {
           sts128(stg_in + uint32_t(lane * 16), rg0);
           if (lane < NOBJ * 4 - 32) sts128(stg_in + uint32_t((lane + 32) * 16), rg1);
+          if (si + 1 < Cfg::SPP) fetch_res(sc + 1);          // lands while this scene is finished and stored
           __syncwarp();
           uint32_t r4[4], r2[2];
           ldsm_x4_t(r4, stg_in + mrow);
