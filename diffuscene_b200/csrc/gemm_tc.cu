@@ -23,6 +23,7 @@
 // transposes exist anywhere in the data path.  A "virtual concat" [A0|A1] (the U-Net skip connections,
 // denoise_net.py:562,566,573) is served by switching tensor maps inside the k loop.
 #include <cuda.h>
+#include <type_traits>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -955,7 +956,6 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     const int chl = 32 * q + 8 * (lane & 3) + (lane >> 2);      // channel (inside the tile) on this thread's lane
     const int gq = q >> 1;                                       // GroupNorm group of the tile (64 channels each)
     const bool film_uni = epi.film.mode == FILM_TIME && epi.film_uniform;
-    const int fmode = epi.film.mode == FILM_OBJECT ? 1 : (epi.film.mode == FILM_TOKEN ? 2 : 0);
     const bool per_scene_t = epi.film.mode == FILM_TIME && !film_uni;
     const float* fr_u = film_uni ? epi.film.base + (int64_t)__ldg(epi.film.t) * epi.film.row_stride : nullptr;
     for (int n = etid; n < epi.N; n += Cfg::EPI_W * 32) {
@@ -980,173 +980,215 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     };
     // coalesced view of a staging block: 16-byte piece `lane` and (for 12 tokens) `lane + 32` of its 48 pieces
     const int cr0 = lane >> 2, cp0 = lane & 3;
+    const bool second = lane < NOBJ * 4 - 32;
+    const int s_begin = part * Cfg::SPP;
+    // tile walk without divisions: (ct, tt) advance by a constant step with carry
+    const int step_ct = int(gridDim.x) % num_ct, step_tt = int(gridDim.x) / num_ct;
     int ab = 0;
     uint32_t aphase = 0;
     unsigned long long tw_tf = 0, tstart = clock64(), ntiles = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int ct = tile % num_ct, tt = tile / num_ct;
-      const int ch = ct * BM + chl;
-      const float bias = bias_s[ch];
-      const float2 gb = gb_s[ch];
-      const float2 fu = film_u[ch];
-      // scene-constant part of y/2 = (acc + bias - mean) * rstd * P + Q   (modes 1, 2: plain affine, FiLM per element)
-      float P = fmode ? gb.x : 0.5f * gb.x * fu.x;
-      float Q = fmode ? gb.y : 0.5f * fmaf(gb.y, fu.x, fu.y);
-      float Fo[NOBJ], Go[NOBJ];                      // per-object FiLM of this channel (context blocks)
-      if (fmode == 1) {
-#pragma unroll
-        for (int j = 0; j < NOBJ; ++j) {
-          const float* fr = epi.film.base + (int64_t)j * epi.film.row_stride + ch;
-          Fo[j] = 0.5f * (__ldg(fr) + 1.0f);
-          Go[j] = 0.5f * __ldg(fr + epi.C);
-        }
-      }
-      const int s_begin = part * Cfg::SPP;
-      // residual rows of this warp's 32 channels for one scene: 48 coalesced 16-byte pieces (lane, lane + 32).
-      // Software-pipelined one scene ahead; the first fetch is issued before the accumulator is even complete.
-      uint4 rg0 = make_uint4(0u, 0u, 0u, 0u), rg1 = rg0;
-      auto fetch_res = [&](int sc) {
-        const int scene_g = tt * Cfg::SC + sc;
-        if (scene_g < n_scenes_total) {
-          const bf16* rb = epi.res + (int64_t)scene_g * NOBJ * epi.ldres + ct * BM + 32 * q;
-          rg0 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)cr0 * epi.ldres + cp0 * 8));
-          if (lane < NOBJ * 4 - 32) rg1 = __ldg(reinterpret_cast<const uint4*>(rb + (int64_t)(cr0 + 8) * epi.ldres + cp0 * 8));
-        }
-      };
-      if (epi.res) fetch_res(s_begin);
-      unsigned long long t0 = epi.trace ? clock64() : 0;
-      mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
-      if (epi.trace) { tw_tf += clock64() - t0; ++ntiles; }
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * Cfg::ACC_STRIDE);
 
-      // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
-      {
-        uint32_t va[12];
-        tmem_ld12_issue(taddr + uint32_t(s_begin * NOBJ), va);
-#pragma unroll
-        for (int si = 0; si < Cfg::SPP; ++si) {
-          const int sc = s_begin + si;
-          tmem_ld12_wait(va);
-          float v[NOBJ];
-#pragma unroll
-          for (int j = 0; j < NOBJ; ++j) v[j] = __uint_as_float(va[j]);
-          if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((sc + 1) * NOBJ), va);
-          float s1 = 0.f, s2 = 0.f;
+    // The tile loop is instantiated per (FiLM mode, residual) so that the per-scene loop carries no mode branches:
+    //   FM 0: scene-constant FiLM (none / batch-uniform timestep)   FM 1: per-object FiLM (context blocks)
+    //   FM 2: per-token FiLM                                        FM 3: per-scene timestep FiLM
+    auto run_tiles = [&](auto fm_tag, auto res_tag) {
+      constexpr int FM = decltype(fm_tag)::value;
+      constexpr bool RES = decltype(res_tag)::value;
+      int ct = int(blockIdx.x) % num_ct, tt = int(blockIdx.x) / num_ct;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int ch = ct * BM + chl;
+        const float bias = bias_s[ch];
+        const float2 gb = gb_s[ch];
+        // scene-constant part of y/2 = (acc + bias - mean) * rstd * P + Q  (FM 1, 2: plain affine, FiLM per element)
+        float P = gb.x, Q = gb.y;
+        if constexpr (FM == 0) {
+          const float2 fu = film_u[ch];
+          P = 0.5f * gb.x * fu.x;
+          Q = 0.5f * fmaf(gb.y, fu.x, fu.y);
+        }
+        float Fo[FM == 1 ? NOBJ : 1], Go[FM == 1 ? NOBJ : 1];     // per-object FiLM of this channel
+        if constexpr (FM == 1) {
 #pragma unroll
           for (int j = 0; j < NOBJ; ++j) {
-            s1 += v[j];
-            s2 = fmaf(v[j], v[j], s2);
+            const float* fr = epi.film.base + (int64_t)j * epi.film.row_stride + ch;
+            Fo[j] = 0.5f * (__ldg(fr) + 1.0f);
+            Go[j] = 0.5f * __ldg(fr + epi.C);
           }
-          const float S = fmaf(float(NOBJ), bias, s1);
-          const float SS = fmaf(bias, fmaf(float(NOBJ), bias, 2.0f * s1), s2);
-          red[sc * 128 + 32 * q + lane] = make_float2(S, SS);
         }
-      }
-      epi_bar();
-      if (etid < Cfg::SC * 2 * 8) {                  // 8 threads per (scene, group): whole warps by construction
-        const int pid = etid >> 3, sub = etid & 7;
-        const float2* rp = red + (pid >> 1) * 128 + (pid & 1) * 64 + sub;
-        float s = 0.f, ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 p2 = rp[8 * i];
-          s += p2.x;
-          ss += p2.y;
+        const int scene0 = tt * Cfg::SC + s_begin;                 // first scene of this warp in this tile
+        const int n_live = n_scenes_total - scene0;                // scenes si < n_live exist
+        const int col0 = ct * BM + 32 * q + cp0 * 8;
+        // piece pointers of scene 0 (rows cr0 and cr0 + 8 of the [token][32 channel] block); + NOBJ rows per scene
+        bf16* dp = epi.d + ((int64_t)scene0 * NOBJ + cr0) * epi.ldd + col0;
+        const bf16* rp = RES ? epi.res + ((int64_t)scene0 * NOBJ + cr0) * epi.ldres + col0 : nullptr;
+        const int64_t d_step = (int64_t)NOBJ * epi.ldd, r_step = (int64_t)NOBJ * epi.ldres;
+        const int64_t d_hi = (int64_t)8 * epi.ldd, r_hi = (int64_t)8 * epi.ldres;
+        // residual: software-pipelined one scene ahead; the first fetch is issued before the accumulator is complete
+        uint4 rg0 = make_uint4(0u, 0u, 0u, 0u), rg1 = rg0;
+        if constexpr (RES) {
+          if (0 < n_live) {
+            rg0 = __ldg(reinterpret_cast<const uint4*>(rp));
+            if (second) rg1 = __ldg(reinterpret_cast<const uint4*>(rp + r_hi));
+          }
         }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        }
-        if (sub == 0) {
-          const float inv = 1.0f / float(NOBJ * 64);
-          const float mean = s * inv;
-          const float var = fmaxf(ss * inv - mean * mean, 0.f);
-          stat[pid] = make_float2(mean, rsqrtf(var + 1e-5f));
-        }
-      }
-      epi_bar();
+        unsigned long long t0 = epi.trace ? clock64() : 0;
+        mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
+        if (epi.trace) { tw_tf += clock64() - t0; ++ntiles; }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * Cfg::ACC_STRIDE + s_begin * NOBJ);
 
-      // ---- pass 2: normalise + FiLM + SiLU (+ residual) per scene, transposed store through the staging blocks
-      uint32_t va[12];
-      tmem_ld12_issue(taddr + uint32_t(s_begin * NOBJ), va);
-#pragma unroll 1
-      for (int si = 0; si < Cfg::SPP; ++si) {
-        const int sc = s_begin + si;
-        const int scene_g = tt * Cfg::SC + sc;
-        const bool live = scene_g < n_scenes_total;
-        const int64_t tok0 = (int64_t)scene_g * NOBJ;
-        float Ps = P, Qs = Q;
-        if (per_scene_t && live) {
-          const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene_g) * epi.film.row_stride + ch;
-          const float fx = __ldg(fr) + 1.0f, fy = __ldg(fr + epi.C);
-          Ps = 0.5f * gb.x * fx;
-          Qs = 0.5f * fmaf(gb.y, fx, fy);
-        }
-        const float2 st = stat[sc * 2 + gq];
-        const float a = st.y * Ps;
-        const float b = fmaf(bias - st.x, a, Qs);
-        tmem_ld12_wait(va);
-        float y[NOBJ];
+        // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
+        {
+          uint32_t va[12];
+          tmem_ld12_issue(taddr, va);
+          float2* rdst = red + s_begin * 128 + 32 * q + lane;
 #pragma unroll
-        for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(__uint_as_float(va[j]), a, b);
-        if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((sc + 1) * NOBJ), va);
-        else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(ab));          // accumulator drained: the next tile's MMAs may start
-        }
-        if (fmode == 1) {
+          for (int si = 0; si < Cfg::SPP; ++si) {
+            tmem_ld12_wait(va);
+            float v[NOBJ];
 #pragma unroll
-          for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(y[j], Fo[j], Go[j]);
-        } else if (fmode == 2) {
-          if (live) {
+            for (int j = 0; j < NOBJ; ++j) v[j] = __uint_as_float(va[j]);
+            if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((si + 1) * NOBJ), va);
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int j = 0; j < NOBJ; ++j) {
-              const float* fr = epi.film.base + (tok0 + j) * epi.film.row_stride + ch;
-              y[j] = 0.5f * fmaf(y[j], __ldg(fr) + 1.0f, __ldg(fr + epi.C));
+              s1 += v[j];
+              s2 = fmaf(v[j], v[j], s2);
+            }
+            const float S = fmaf(float(NOBJ), bias, s1);
+            const float SS = fmaf(bias, fmaf(float(NOBJ), bias, 2.0f * s1), s2);
+            rdst[si * 128] = make_float2(S, SS);
+          }
+        }
+        epi_bar();
+        if (etid < Cfg::SC * 2 * 8) {                  // 8 threads per (scene, group): whole warps by construction
+          const int pid = etid >> 3, sub = etid & 7;
+          const float2* rsrc = red + (pid >> 1) * 128 + (pid & 1) * 64 + sub;
+          float s = 0.f, ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 p2 = rsrc[8 * i];
+            s += p2.x;
+            ss += p2.y;
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          }
+          if (sub == 0) {
+            const float inv = 1.0f / float(NOBJ * 64);
+            const float mean = s * inv;
+            const float var = fmaxf(ss * inv - mean * mean, 0.f);
+            stat[pid] = make_float2(mean, rsqrtf(var + 1e-5f));
+          }
+        }
+        epi_bar();
+
+        // ---- pass 2: normalise + FiLM + SiLU (+ residual) per scene, transposed store through the staging blocks
+        uint32_t va[12];
+        tmem_ld12_issue(taddr, va);
+        const float2* stp = stat + s_begin * 2 + gq;
+#pragma unroll 1
+        for (int si = 0; si < Cfg::SPP; ++si) {
+          const bool live = si < n_live;
+          float Ps = P, Qs = Q;
+          if constexpr (FM == 3) {
+            if (live) {
+              const float* fr = epi.film.base + (int64_t)__ldg(epi.film.t + scene0 + si) * epi.film.row_stride + ch;
+              const float fx = __ldg(fr) + 1.0f, fy = __ldg(fr + epi.C);
+              Ps = 0.5f * gb.x * fx;
+              Qs = 0.5f * fmaf(gb.y, fx, fy);
             }
           }
-        }
+          const float2 st = stp[2 * si];
+          const float a = st.y * Ps;
+          const float b = fmaf(bias - st.x, a, Qs);
+          tmem_ld12_wait(va);
+          float y[NOBJ];
 #pragma unroll
-        for (int j = 0; j < NOBJ; ++j) y[j] = silu_from_half(y[j]);
-        if (epi.res) {
-          sts128(stg_in + uint32_t(lane * 16), rg0);
-          if (lane < NOBJ * 4 - 32) sts128(stg_in + uint32_t((lane + 32) * 16), rg1);
-          if (si + 1 < Cfg::SPP) fetch_res(sc + 1);          // lands while this scene is finished and stored
-          __syncwarp();
-          uint32_t r4[4], r2[2];
-          ldsm_x4_t(r4, stg_in + mrow);
-          ldsm_x2_t(r2, stg_in + 512u + mrow);        // lanes 0-15 address tokens 8..11
-          const uint32_t rr[6] = {r4[0], r4[1], r4[2], r4[3], r2[0], r2[1]};
+          for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(__uint_as_float(va[j]), a, b);
+          if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((si + 1) * NOBJ), va);
+          else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(ab));          // accumulator drained: the next tile's MMAs may start
+          }
+          if constexpr (FM == 1) {
+#pragma unroll
+            for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(y[j], Fo[j], Go[j]);
+          }
+          if constexpr (FM == 2) {
+            if (live) {
+#pragma unroll
+              for (int j = 0; j < NOBJ; ++j) {
+                const float* fr = epi.film.base + ((int64_t)(scene0 + si) * NOBJ + j) * epi.film.row_stride + ch;
+                y[j] = 0.5f * fmaf(y[j], __ldg(fr) + 1.0f, __ldg(fr + epi.C));
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NOBJ; ++j) y[j] = silu_from_half(y[j]);
+          if constexpr (RES) {
+            sts128(stg_in + uint32_t(lane * 16), rg0);
+            if (second) sts128(stg_in + uint32_t((lane + 32) * 16), rg1);
+            rp += r_step;
+            if (si + 1 < Cfg::SPP && si + 1 < n_live) {          // next scene's rows land while this one is finished
+              rg0 = __ldg(reinterpret_cast<const uint4*>(rp));
+              if (second) rg1 = __ldg(reinterpret_cast<const uint4*>(rp + r_hi));
+            }
+            __syncwarp();
+            uint32_t r4[4], r2[2];
+            ldsm_x4_t(r4, stg_in + mrow);
+            ldsm_x2_t(r2, stg_in + 512u + mrow);        // lanes 0-15 address tokens 8..11
+            const uint32_t rr[6] = {r4[0], r4[1], r4[2], r4[3], r2[0], r2[1]};
+#pragma unroll
+            for (int i = 0; i < NOBJ / 2; ++i) {
+              y[2 * i] += __uint_as_float(rr[i] << 16);
+              y[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+            }
+          }
+          uint32_t pk[NOBJ / 2];
 #pragma unroll
           for (int i = 0; i < NOBJ / 2; ++i) {
-            y[2 * i] += __uint_as_float(rr[i] << 16);
-            y[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
           }
-        }
-        uint32_t pk[NOBJ / 2];
-#pragma unroll
-        for (int i = 0; i < NOBJ / 2; ++i) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
-          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        stsm_x4_t(stg_out + mrow, pk[0], pk[1], pk[2], pk[3]);
-        stsm_x2_t(stg_out + 512u + mrow, pk[4], pk[5]);
-        __syncwarp();
-        if (live) {
-          bf16* db = epi.d + tok0 * epi.ldd + ct * BM + 32 * q;
-          const uint4 o0 = lds128(stg_out + uint32_t(lane * 16));
-          *reinterpret_cast<uint4*>(db + (int64_t)cr0 * epi.ldd + cp0 * 8) = o0;
-          if (lane < NOBJ * 4 - 32) {
-            const uint4 o1 = lds128(stg_out + uint32_t((lane + 32) * 16));
-            *reinterpret_cast<uint4*>(db + (int64_t)(cr0 + 8) * epi.ldd + cp0 * 8) = o1;
+          stsm_x4_t(stg_out + mrow, pk[0], pk[1], pk[2], pk[3]);
+          stsm_x2_t(stg_out + 512u + mrow, pk[4], pk[5]);
+          __syncwarp();
+          if (live) {
+            const uint4 o0 = lds128(stg_out + uint32_t(lane * 16));
+            *reinterpret_cast<uint4*>(dp) = o0;
+            if (second) {
+              const uint4 o1 = lds128(stg_out + uint32_t((lane + 32) * 16));
+              *reinterpret_cast<uint4*>(dp + d_hi) = o1;
+            }
           }
+          dp += d_step;
+          __syncwarp();
         }
-        __syncwarp();
+        if (++ab == 2) { ab = 0; aphase ^= 1u; }
+        ct += step_ct;
+        tt += step_tt;
+        if (ct >= num_ct) { ct -= num_ct; ++tt; }
       }
-      if (++ab == 2) { ab = 0; aphase ^= 1u; }
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    const int fm = epi.film.mode == FILM_OBJECT ? 1 : (epi.film.mode == FILM_TOKEN ? 2 : (per_scene_t ? 3 : 0));
+    if (epi.res) {
+      if (fm == 0) run_tiles(I0{}, std::true_type{});
+      else if (fm == 1) run_tiles(I1{}, std::true_type{});
+      else if (fm == 2) run_tiles(I2{}, std::true_type{});
+      else run_tiles(I3{}, std::true_type{});
+    } else {
+      if (fm == 0) run_tiles(I0{}, std::false_type{});
+      else if (fm == 1) run_tiles(I1{}, std::false_type{});
+      else if (fm == 2) run_tiles(I2{}, std::false_type{});
+      else run_tiles(I3{}, std::false_type{});
     }
     if (epi.trace && warp == 2 && lane == 0) {
       epi.trace[blockIdx.x * 8 + 5] = tw_tf;
