@@ -44,6 +44,7 @@ struct ds_handle {
   bool taps = false;
   bool bf16_mode = false, use_tc = false;
   bool gnt = false;      // fused GroupNorm convs run the channels-on-lanes kernel (weights stored row-permuted)
+  bool gnt_plain = false;   // ... and so do the plain GEMMs with N % 128 == 0 (fuse_level 3)
   size_t esz = 4;
   cudaStream_t own_stream = nullptr;
   std::map<std::string, std::vector<float>> host_w;
@@ -198,6 +199,20 @@ static void free_buffers(ds_handle* h) {
   h->cap_scenes = 0;
 }
 
+// which kernel variant a GEMM op runs on (0: row-major tcgen05 kernel, 2: channels-on-lanes GroupNorm, 3: ... plain)
+static int gemm_variant(const ds_handle* h, const Op& o) {
+  if (o.kind == OP_GEMM_GN) return h->gnt ? 2 : 1;
+  // plain GEMMs: the channels-on-lanes kernel wins where the epilogue dominates (K <= 128: to_out) or where the
+  // row-major kernel would fall back to 128-wide tiles (N % 256 != 0: to_qkv); the MMA-bound shapes keep the
+  // row-major kernel, whose 128 x 256 tiles feed the tensor pipe better than 128 x 192 (measured, profiles/)
+  if (o.kind == OP_GEMM && h->gnt_plain && tc_gnt_plain_supported(h->cfg.num_objects, o.N)) {
+    static const int force_all = getenv("DS_GNT_PLAIN_ALL") ? atoi(getenv("DS_GNT_PLAIN_ALL")) : 0;
+    const int K = o.in0.k + (o.in1.buf >= 0 ? o.in1.k : 0);
+    if (force_all || K <= 128 || o.N % 256 != 0) return 3;
+  }
+  return 0;
+}
+
 static int ensure_capacity(ds_handle* h, int n_scenes) {
   if (n_scenes <= 0) return fail(DS_ERR_INVALID, "batch must be positive");
   if (!h->committed) return fail(DS_ERR_STATE, "ds_commit_weights() has not been called");
@@ -227,8 +242,10 @@ static int ensure_capacity(ds_handle* h, int n_scenes) {
       auto ptr = [&](int buf, int col) -> bf16* { return buf < 0 ? nullptr : (bf16*)h->bufs[buf] + col; };
       GemmArgs g;
       memset(&g, 0, sizeof g);
+      g.gn = gemm_variant(h, o);
+      g.n_obj = n_obj;
       if (o.kind == OP_GEMM_GN) {
-        g.gn = h->gnt ? 2 : 1; g.n_obj = n_obj; g.film_C = P.C;
+        g.film_C = P.C;
         g.gamma = h->varena + h->v_off[o.gamma];
         g.beta = h->varena + h->v_off[o.beta];
         g.film = film_ref(h, o);
@@ -331,8 +348,14 @@ extern "C" int ds_commit_weights(ds_handle* h) {
   std::vector<char> host(total, 0);
   std::vector<float> mat;
   std::vector<char> gnt_w(P.wmats.size(), 0);       // weight matrices consumed by fused GroupNorm ops
-  for (const Op& o : P.ops)
-    if (o.kind == OP_GEMM_GN) gnt_w[o.w] = 1;
+  std::vector<char> row_major_w(P.wmats.size(), 0);
+  for (const Op& o : P.ops) {
+    if (o.kind != OP_GEMM && o.kind != OP_GEMM_GN) continue;
+    if (gemm_variant(h, o) >= 2) gnt_w[o.w] = 1;
+    else row_major_w[o.w] = 1;
+  }
+  for (size_t i = 0; i < P.wmats.size(); ++i)
+    if (gnt_w[i] && row_major_w[i]) return fail(DS_ERR_STATE, "weight matrix %d is shared by both GEMM layouts", int(i));
   for (size_t i = 0; i < P.wmats.size(); ++i) {
     const WRecipe& r = P.wmats[i];
     mat.assign((size_t)r.N * r.K, 0.f);
@@ -357,7 +380,7 @@ extern "C" int ds_commit_weights(ds_handle* h) {
         }
       }
     }
-    if (h->gnt && gnt_w[i]) {      // row order the channels-on-lanes kernel expects (see tc_gnt_row)
+    if (gnt_w[i]) {      // row order the channels-on-lanes kernel expects (see tc_gnt_row)
       std::vector<float> pm(mat.size());
       for (int rr = 0; rr < r.N; ++rr) memcpy(pm.data() + (size_t)rr * r.K, mat.data() + (size_t)tc_gnt_row(rr) * r.K, sizeof(float) * r.K);
       mat.swap(pm);
@@ -481,6 +504,7 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   // fuse_level 2: the fused conv + GroupNorm ops use the channels-on-lanes tcgen05 kernel where it applies
   h->gnt = h->use_tc && cfg->fuse_level >= 2 && tc_gnt_supported(cfg->num_objects, h->plan.C);
   if (const char* e = getenv("DS_GNT")) h->gnt = h->gnt && atoi(e) != 0;
+  h->gnt_plain = h->gnt && cfg->fuse_level >= 3;
   cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete h;
@@ -1085,9 +1109,11 @@ extern "C" int ds_test_gemm_trace(const void* a_dev, const void* w_dev, const fl
   g.a0 = a_dev; g.lda0 = K; g.k0 = K; g.w = w_dev; g.ldw = K; g.bias = bias_dev; g.d = d_dev; g.ldd = N;
   g.res = res_dev; g.ldres = N; g.M = M; g.N = N;
   // n_obj < 0: the channels-on-lanes variant (the caller passes the weight rows in tc_gnt_row order)
+  // ... and n_obj < 0 with gamma == NULL: the same kernel as a plain GEMM (act passed in `reps` bits 8.. for the probe)
   if (n_obj != 0) {
-    g.gn = n_obj < 0 ? 2 : 1; g.n_obj = n_obj < 0 ? -n_obj : n_obj; g.film_C = N; g.gamma = gamma_dev; g.beta = beta_dev;
-    g.film.mode = FILM_NONE;
+    g.gn = n_obj < 0 ? (gamma_dev ? 2 : 3) : 1; g.n_obj = n_obj < 0 ? -n_obj : n_obj; g.film_C = N; g.gamma = gamma_dev;
+    g.beta = beta_dev; g.film.mode = FILM_NONE;
+    if (g.gn == 3) { g.act = reps >> 8; reps &= 0xff; }
   }
   char err[256] = "";
   TcGemmPlan* p = tc_plan_create(g, M, err, sizeof err);

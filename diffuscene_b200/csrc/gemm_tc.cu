@@ -56,6 +56,7 @@ struct TcEpi {
   const float* beta;
   FilmRef film;
   int film_uniform;      // FILM_TIME only: t[] holds one value for the whole launch (sampling loop)
+  int plain;             // channels-on-lanes kernel without GroupNorm: bias, activation, residual only
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
 };
 // trace slots: 0 producer wait-empty, 1 producer total, 2 mma wait-tmem-empty, 3 mma wait-full, 4 mma total,
@@ -958,12 +959,14 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     const bool film_uni = epi.film.mode == FILM_TIME && epi.film_uniform;
     const bool per_scene_t = epi.film.mode == FILM_TIME && !film_uni;
     const float* fr_u = film_uni ? epi.film.base + (int64_t)__ldg(epi.film.t) * epi.film.row_stride : nullptr;
-    for (int n = etid; n < epi.N; n += Cfg::EPI_W * 32) {
-      bias_s[n] = epi.bias ? __ldg(epi.bias + n) : 0.f;
-      gb_s[n] = make_float2(__ldg(epi.gamma + n), __ldg(epi.beta + n));
-      film_u[n] = film_uni ? make_float2(__ldg(fr_u + n) + 1.0f, __ldg(fr_u + epi.C + n)) : make_float2(1.0f, 0.0f);
+    if (!epi.plain) {      // per-channel tables of the GroupNorm epilogue (N <= 512); plain GEMMs read their bias directly
+      for (int n = etid; n < epi.N; n += Cfg::EPI_W * 32) {
+        bias_s[n] = epi.bias ? __ldg(epi.bias + n) : 0.f;
+        gb_s[n] = make_float2(__ldg(epi.gamma + n), __ldg(epi.beta + n));
+        film_u[n] = film_uni ? make_float2(__ldg(fr_u + n) + 1.0f, __ldg(fr_u + epi.C + n)) : make_float2(1.0f, 0.0f);
+      }
+      epi_bar();
     }
-    epi_bar();
     // staging blocks of this warp: [token][32 channels] bf16, 64 B rows
     const uint32_t stg_in = base + uint32_t(Cfg::STG_OFF) + uint32_t((warp - 2) * 2 * Cfg::STG_BYTES);
     const uint32_t stg_out = stg_in + uint32_t(Cfg::STG_BYTES);
@@ -991,14 +994,21 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     // The tile loop is instantiated per (FiLM mode, residual) so that the per-scene loop carries no mode branches:
     //   FM 0: scene-constant FiLM (none / batch-uniform timestep)   FM 1: per-object FiLM (context blocks)
     //   FM 2: per-token FiLM                                        FM 3: per-scene timestep FiLM
+    //   FM 4: no GroupNorm at all (plain GEMM: bias, GELU / SiLU, residual) -- no statistics pass, no barriers
     auto run_tiles = [&](auto fm_tag, auto res_tag) {
       constexpr int FM = decltype(fm_tag)::value;
       constexpr bool RES = decltype(res_tag)::value;
       int ct = int(blockIdx.x) % num_ct, tt = int(blockIdx.x) / num_ct;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int ch = ct * BM + chl;
-        const float bias = bias_s[ch];
-        const float2 gb = gb_s[ch];
+        float bias;
+        float2 gb = make_float2(1.0f, 0.0f);
+        if constexpr (FM == 4) {
+          bias = epi.bias ? __ldg(epi.bias + ch) : 0.f;
+        } else {
+          bias = bias_s[ch];
+          gb = gb_s[ch];
+        }
         // scene-constant part of y/2 = (acc + bias - mean) * rstd * P + Q  (FM 1, 2: plain affine, FiLM per element)
         float P = gb.x, Q = gb.y;
         if constexpr (FM == 0) {
@@ -1038,7 +1048,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * Cfg::ACC_STRIDE + s_begin * NOBJ);
 
         // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
-        {
+        if constexpr (FM != 4) {
           uint32_t va[12];
           tmem_ld12_issue(taddr, va);
           float2* rdst = red + s_begin * 128 + 32 * q + lane;
@@ -1060,8 +1070,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             rdst[si * 128] = make_float2(S, SS);
           }
         }
-        epi_bar();
-        if (etid < Cfg::SC * 2 * 8) {                  // 8 threads per (scene, group): whole warps by construction
+        if constexpr (FM != 4) epi_bar();
+        if (FM != 4 && etid < Cfg::SC * 2 * 8) {                  // 8 threads per (scene, group): whole warps by construction
           const int pid = etid >> 3, sub = etid & 7;
           const float2* rsrc = red + (pid >> 1) * 128 + (pid & 1) * 64 + sub;
           float s = 0.f, ss = 0.f;
@@ -1083,7 +1093,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             stat[pid] = make_float2(mean, rsqrtf(var + 1e-5f));
           }
         }
-        epi_bar();
+        if constexpr (FM != 4) epi_bar();
 
         // ---- pass 2: normalise + FiLM + SiLU (+ residual) per scene, transposed store through the staging blocks
         uint32_t va[12];
@@ -1101,13 +1111,16 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
               Qs = 0.5f * fmaf(gb.y, fx, fy);
             }
           }
-          const float2 st = stp[2 * si];
-          const float a = st.y * Ps;
-          const float b = fmaf(bias - st.x, a, Qs);
+          float a = 1.0f, b = bias;
+          if constexpr (FM != 4) {
+            const float2 st = stp[2 * si];
+            a = st.y * Ps;
+            b = fmaf(bias - st.x, a, Qs);
+          }
           tmem_ld12_wait(va);
           float y[NOBJ];
 #pragma unroll
-          for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(__uint_as_float(va[j]), a, b);
+          for (int j = 0; j < NOBJ; ++j) y[j] = FM == 4 ? __uint_as_float(va[j]) + b : fmaf(__uint_as_float(va[j]), a, b);
           if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((si + 1) * NOBJ), va);
           else {
             tc_fence_before();
@@ -1127,8 +1140,18 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
               }
             }
           }
+          if constexpr (FM == 4) {
+            if (epi.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < NOBJ; ++j) y[j] = silu_from_half(y[j]);
+              for (int j = 0; j < NOBJ; ++j) y[j] = gelu_tanh(y[j]);
+            } else if (epi.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < NOBJ; ++j) y[j] = silu_tanh(y[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NOBJ; ++j) y[j] = silu_from_half(y[j]);
+          }
           if constexpr (RES) {
             sts128(stg_in + uint32_t(lane * 16), rg0);
             if (second) sts128(stg_in + uint32_t((lane + 32) * 16), rg1);
@@ -1178,8 +1201,12 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     using I1 = std::integral_constant<int, 1>;
     using I2 = std::integral_constant<int, 2>;
     using I3 = std::integral_constant<int, 3>;
-    const int fm = epi.film.mode == FILM_OBJECT ? 1 : (epi.film.mode == FILM_TOKEN ? 2 : (per_scene_t ? 3 : 0));
-    if (epi.res) {
+    using I4 = std::integral_constant<int, 4>;
+    const int fm = epi.plain ? 4 : (epi.film.mode == FILM_OBJECT ? 1 : (epi.film.mode == FILM_TOKEN ? 2 : (per_scene_t ? 3 : 0)));
+    if (fm == 4) {
+      if (epi.res) run_tiles(I4{}, std::true_type{});
+      else run_tiles(I4{}, std::false_type{});
+    } else if (epi.res) {
       if (fm == 0) run_tiles(I0{}, std::true_type{});
       else if (fm == 1) run_tiles(I1{}, std::true_type{});
       else if (fm == 2) run_tiles(I2{}, std::true_type{});
@@ -1289,17 +1316,22 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     if (err) snprintf(err, err_len, "tcgen05 GEMM needs 16-byte aligned operands and pitches");
     return nullptr;
   }
-  const bool gn = g.gn != 0;
-  const bool gnt = g.gn == 2;
-  if (gnt && !tc_gnt_supported(g.n_obj, g.N)) {
+  const bool plain_t = g.gn == 3;                 // channels-on-lanes kernel, no GroupNorm
+  const bool gn = g.gn != 0 && !plain_t;
+  const bool gnt = g.gn == 2 || plain_t;
+  if (g.gn == 2 && !tc_gnt_supported(g.n_obj, g.N)) {
     if (err) snprintf(err, err_len, "channels-on-lanes GroupNorm GEMM needs n_obj == 12 and N %% 128 == 0, N <= 512");
+    return nullptr;
+  }
+  if (plain_t && !tc_gnt_plain_supported(g.n_obj, g.N)) {
+    if (err) snprintf(err, err_len, "channels-on-lanes GEMM needs n_obj == 12 and N %% 128 == 0");
     return nullptr;
   }
   if (gn && (g.N % 256 || g.N > TcCfg<256, true>::CHAN_MAX_N || g.n_obj < 1 || g.n_obj > 128 || !g.gamma || !g.beta)) {
     if (err) snprintf(err, err_len, "fused GroupNorm epilogue needs N%%256==0, N<=512, 1<=n_obj<=128, gamma/beta");
     return nullptr;
   }
-  if (!gn && g.N > TcCfg<256, false>::CHAN_MAX_N) {
+  if (!gn && !plain_t && g.N > TcCfg<256, false>::CHAN_MAX_N) {
     if (err) snprintf(err, err_len, "tcgen05 GEMM supports N <= 4096 (N=%d)", g.N);
     return nullptr;
   }
@@ -1347,6 +1379,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.gamma = g.gamma;
   p->epi.beta = g.beta;
   p->epi.film = g.film;
+  p->epi.plain = plain_t ? 1 : 0;
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
   if (const char* e = getenv("DS_TC_IDESC")) p->epi.idesc = (uint32_t)strtoul(e, nullptr, 16);
@@ -1395,6 +1428,7 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
 }
 
+bool tc_gnt_plain_supported(int n_obj, int N) { return n_obj == 12 && N % BM == 0; }
 bool tc_gnt_supported(int n_obj, int N) { return n_obj == 12 && N % BM == 0 && N <= GntCfg<12>::CHAN_MAX_N; }
 
 static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cudaStream_t s) {

@@ -121,6 +121,8 @@ bool tc_runtime_available(char* err, int err_len);
 // GemmArgs.gn == 2 selects the channels-on-lanes GroupNorm GEMM: weight rows must be stored permuted inside every
 // block of 32 output channels (stored row 32 b + l holds channel 32 b + 8 (l % 4) + l / 4)
 bool tc_gnt_supported(int n_obj, int N);
+// GemmArgs.gn == 3: the same kernel as a plain GEMM (bias, activation, residual); same weight row order
+bool tc_gnt_plain_supported(int n_obj, int N);
 inline int tc_gnt_row(int stored_row) { const int l = stored_row & 31; return (stored_row & ~31) + 8 * (l & 3) + (l >> 2); }
 
 }  // namespace ds

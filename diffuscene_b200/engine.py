@@ -41,7 +41,8 @@ class DenoiserEngine:
         if fuse_level is None:      # fused GEMM epilogues exist for the tcgen05 path only
             # 2: conv + GroupNorm GEMMs with the channels on the TMEM lanes where the library supports the shape
             # (N = 12 objects), the row-major fused kernel (level 1) otherwise
-            fuse_level = 2 if (precision == "bf16" and gemm_backend != "simt") else 0
+            # 3: ... and the epilogue-bound plain GEMMs (to_qkv, to_out) on the same kernel
+            fuse_level = 3 if (precision == "bf16" and gemm_backend != "simt") else 0
         self.fuse_level = fuse_level
         self.cfg = capi.make_config(spec, num_objects, num_timesteps, _PREC[precision], _BACKEND[gemm_backend],
                                     device, fuse_level)

@@ -70,7 +70,8 @@ typedef struct ds_config {
   int32_t gemm_backend;     /* ds_gemm_backend                                         */
   int32_t device;           /* CUDA device ordinal                                     */
   int32_t fuse_level;       /* 0: one kernel per op; 1: fused GEMM epilogues; 2: + the
-                               channels-on-lanes conv+GroupNorm GEMM where supported    */
+                               channels-on-lanes conv+GroupNorm GEMM where supported;
+                               3: + epilogue-bound plain GEMMs on that kernel           */
   int32_t reserved[7];
 } ds_config;
 

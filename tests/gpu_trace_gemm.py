@@ -34,7 +34,8 @@ def reference(a, w, bias, gamma, beta, r, n_obj):
     return y
 
 
-def run(M, N, K, n_obj=0, res=False, tag="", gnt=False, check=False):
+def run(M, N, K, n_obj=0, res=False, tag="", gnt=False, check=False, plain_act=None):
+    """plain_act (0 none / 1 GELU / 2 SiLU) with gnt=True: the channels-on-lanes kernel as a plain GEMM"""
     g = torch.Generator().manual_seed(0)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
@@ -46,14 +47,21 @@ def run(M, N, K, n_obj=0, res=False, tag="", gnt=False, check=False):
     tr = np.zeros((256, 8), dtype=np.uint64)
     us = C.c_float()
     w_dev = w[gnt_rows(N).cuda()].contiguous() if gnt else w
+    plain = plain_act is not None
     rc = lib.ds_test_gemm_trace(a.data_ptr(), w_dev.data_ptr(), bias.data_ptr(), None if r is None else r.data_ptr(),
-                                d.data_ptr(), M, N, K, -n_obj if gnt else n_obj, gamma.data_ptr(), beta.data_ptr(), 20,
+                                d.data_ptr(), M, N, K, -n_obj if gnt else n_obj, None if plain else gamma.data_ptr(),
+                                None if plain else beta.data_ptr(), 20 | ((plain_act or 0) << 8),
                                 tr.ctypes.data, C.byref(us))
     if rc:
         print("FAILED", lib.ds_last_error().decode())
         return
     if check:
-        ref = reference(a, w, bias, gamma, beta, r, n_obj)
+        if plain:
+            ref = a.float() @ w.float().t() + bias
+            ref = [lambda z: z, torch.nn.functional.gelu, torch.nn.functional.silu][plain_act](ref)
+            ref = ref + r.float() if r is not None else ref
+        else:
+            ref = reference(a, w, bias, gamma, beta, r, n_obj)
         err = (d.float() - ref).abs()
         bad = (err > 0.05 + 0.02 * ref.abs()).sum().item()
         print("   check %-20s max|err|=%.4f mean|err|=%.5f  out-of-tolerance=%d  %s" % (
@@ -77,6 +85,23 @@ if os.environ.get("GNT_ONLY"):
         run(m_chk, 512, 512, n_obj=12, tag="GNT", gnt=True, check=True)
         run(m_chk, 512, 512, n_obj=12, res=True, tag="GNT+res", gnt=True, check=True)
         run(m_chk, 512, 1024, n_obj=12, res=True, tag="GNT+res K=1024", gnt=True, check=True)
+    for m_chk in (12 * 16 * 3, 12 * 1000):
+        run(m_chk, 512, 128, n_obj=12, tag="T plain K=128", gnt=True, check=True, plain_act=0)
+        run(m_chk, 384, 512, n_obj=12, tag="T plain N=384", gnt=True, check=True, plain_act=0)
+        run(m_chk, 1536, 64, n_obj=12, tag="T gelu N=1536 K=64", gnt=True, check=True, plain_act=1)
+        run(m_chk, 512, 512, n_obj=12, res=True, tag="T silu+res", gnt=True, check=True, plain_act=2)
+    run(M, 512, 128, n_obj=12, tag="T to_out K=128", gnt=True, plain_act=0)
+    run(M, 384, 512, n_obj=12, tag="T qkv N=384", gnt=True, plain_act=0)
+    run(M, 1536, 64, n_obj=12, tag="T enc.l0 gelu", gnt=True, plain_act=1)
+    run(M, 1024, 512, n_obj=12, tag="T enc.l1 gelu", gnt=True, plain_act=1)
+    run(M, 3072, 512, n_obj=12, tag="T dec.l0 gelu", gnt=True, plain_act=1)
+    run(M, 512, 1024, n_obj=12, tag="T res_conv K=1024", gnt=True, plain_act=0)
+    run(M, 512, 128, tag="to_out K=128")
+    run(M, 384, 512, tag="qkv (BN=128)")
+    run(M, 1536, 64, tag="enc.l0")
+    run(M, 1024, 512, tag="enc.l1")
+    run(M, 3072, 512, tag="dec.l0")
+    run(M, 512, 1024, tag="plain 512x1024")
     run(M, 512, 512, n_obj=12, tag="GNT", gnt=True)
     run(M, 512, 512, n_obj=12, res=True, tag="GNT+res", gnt=True)
     run(M, 512, 1024, n_obj=12, res=True, tag="GNT+res K=1024", gnt=True)

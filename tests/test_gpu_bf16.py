@@ -72,13 +72,16 @@ def test_fused_groupnorm_epilogue_matches_unfused(name, golden_dir):
     assert (a - g).abs().mean() <= (b - g).abs().mean() * 1.5 + 1e-4
 
 
+@pytest.mark.parametrize("fuse", [2, 3])
 @pytest.mark.parametrize("name", ["bed62", "bed97", "text62", "arr5", "obj29"])
-def test_channels_on_lanes_groupnorm_gemm(name, golden_dir):
+def test_channels_on_lanes_groupnorm_gemm(name, fuse, golden_dir):
     """fuse_level 2 (the conv + GroupNorm GEMM with the output channels on the TMEM lanes, weights stored
     row-permuted) against the golden forward and against fuse_level 1: same math, different tiling.  Covers the
     uniform-free per-scene FiLM (forward with per-scene t), the per-object FiLM of the context blocks, the
-    two-operand skip convs and the residual path.  Cases with N != 12 objects keep the row-major kernel."""
-    e2, case, spec, inp = get_engine(name, "bf16", "tcgen05", fuse=2)
+    two-operand skip convs and the residual path.  fuse_level 3 also routes every plain GEMM with N % 128 == 0
+    (encoder / decoder MLPs, qkv, to_out, res_conv, down / up convs) to the same kernel.  Cases with N != 12 objects
+    keep the row-major kernels."""
+    e2, case, spec, inp = get_engine(name, "bf16", "tcgen05", fuse=fuse)
     e1, _, _, _ = get_engine(name, "bf16", "tcgen05", fuse=1)
     g = torch.from_numpy(gold(golden_dir, name)["fwd"])
     a = e2.forward(cuda(inp["x"]), cuda(inp["t"])).cpu()
@@ -89,10 +92,11 @@ def test_channels_on_lanes_groupnorm_gemm(name, golden_dir):
     assert (a - g).abs().mean() <= (b - g).abs().mean() * 1.5 + 1e-4
 
 
-def test_channels_on_lanes_sampling_and_batch_independence(golden_dir):
+@pytest.mark.parametrize("fuse", [2, 3])
+def test_channels_on_lanes_sampling_and_batch_independence(fuse, golden_dir):
     """fuse_level 2 in the sampling loop (batch-uniform FiLM staged per kernel) at a batch with a ragged last
     tile, against the fp32 golden loop; scenes are independent of the batch they are in."""
-    eng, case, spec, inp = get_engine("bed62_loop", "bf16", "tcgen05", fuse=2)
+    eng, case, spec, inp = get_engine("bed62_loop", "bf16", "tcgen05", fuse=fuse)
     g = gold(golden_dir, "bed62_loop")
     T = case["diffusion_kwargs"]["time_num"]
     shape = tuple(inp["x"].shape)
