@@ -238,30 +238,42 @@ def main():
                          "launch": "one diffusion step (CUDA graph of the step program) over %d scenes; "
                                    "algorithmic 870.3 MFLOP/scene/step" % B},
         }
-        # dominant kernel (the fused 1x1-conv + GroupNorm + FiLM + SiLU tcgen05 GEMM), timed live with CUDA events
-        # around each op of one eager pass of the step program; DRAM traffic from the committed ncu capture
+        # dominant kernel: k_gemm_gnt<12>, the channels-on-lanes tcgen05 GEMM that carries the 56 fused conv + GroupNorm
+        # + FiLM + SiLU blocks and the epilogue-bound plain GEMMs (to_qkv, to_out) -- 76 of the 125 launches of a step.
+        # Timed live with CUDA events around each op of one eager pass of the step program (launching stream);
+        # DRAM traffic from the committed ncu capture of the same command.
         from diffuscene_b200 import capi
         ops = eng.profile_ops(B)
-        plan_ops = [o for o in capi.plan_export(eng.cfg)["ops"]]
         us_by_name = dict(ops)
-        gn = [o for o in plan_ops if o["kind"] == 7 and o["name"] in us_by_name]
-        if gn:
-            gn_us = sum(us_by_name[o["name"]] for o in gn) / len(gn)
-            gn_flop = sum(2.0 * B * N_OBJ * o["N"] * (o["in0"]["k"] + o["in1"]["k"]) for o in gn) / len(gn)
+
+        def on_gnt(o):      # mirrors gemm_variant() in csrc/engine.cu
+            if eng.fuse_level < 2 or N_OBJ != 12 or o["name"] not in us_by_name:
+                return False
+            if o["kind"] == 7:
+                return True
+            k = o["in0"]["k"] + o["in1"]["k"]
+            return o["kind"] == 1 and eng.fuse_level >= 3 and o["N"] % 128 == 0 and (k <= 128 or o["N"] % 256 != 0)
+
+        dom = [o for o in capi.plan_export(eng.cfg)["ops"] if on_gnt(o)]
+        if dom:
+            dom_us = sum(us_by_name[o["name"]] for o in dom)
+            dom_flop = sum(2.0 * B * N_OBJ * o["N"] * (o["in0"]["k"] + o["in1"]["k"]) for o in dom)
             res["roofline"]["dominant_kernel"] = {
-                "name": "k_gemm_tc<256,1> (GEMM + GroupNorm/FiLM/SiLU epilogue)", "launches_per_step": len(gn),
-                "avg_us": gn_us, "achieved": gn_flop / (gn_us * 1e-6) / 1e12, "unit": "TFLOP/s",
-                "frac": gn_flop / (gn_us * 1e-6) / 1e12 / peak_tf,
-                "share_of_step": sum(us_by_name[o["name"]] for o in gn) / max(1e-9, sum(u for _, u in ops))}
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "round1_v6_dram_traffic.json")
-        if B == 4096 and args.precision == "bf16" and os.path.exists(tpath):
+                "name": "k_gemm_gnt<12> (tcgen05 GEMM, output channels on the TMEM lanes; conv+GroupNorm+FiLM+SiLU "
+                        "epilogue for 56 launches, bias-only for 20)", "launches_per_step": len(dom),
+                "avg_us": dom_us / len(dom), "achieved": dom_flop / (dom_us * 1e-6) / 1e12, "unit": "TFLOP/s",
+                "frac": dom_flop / (dom_us * 1e-6) / 1e12 / peak_tf,
+                "share_of_step": dom_us / max(1e-9, sum(u for _, u in ops))}
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "round1_v8_dram_traffic.json")
+        if B == 4096 and args.precision == "bf16" and eng.fuse_level >= 3 and os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
             res["roofline"]["traffic"] = tj["step_dram_bytes"]
-            res["roofline"]["traffic_source"] = "profiles/round1_v6_dram_traffic.json (ncu dram__bytes_read+write, one step)"
-            k = tj["kernels"].get("k_gemm_tc<256, 1>")
-            if k and gn:
+            res["roofline"]["traffic_source"] = "profiles/round1_v8_dram_traffic.json (ncu dram__bytes_read+write, one step)"
+            k = tj["kernels"].get("k_gemm_gnt<12>")
+            if k and dom:
                 res["roofline"]["dominant_kernel"]["traffic"] = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"]
+                res["roofline"]["dominant_kernel"]["ncu_share_of_step"] = k["time_ns"] / tj["step_time_ns"]
         if args.profile_ops:
             tot = sum(u for _, u in ops)
             gemm = sum(u for n, u in ops if "proj" in n or "conv" in n or n.startswith(("enc", "dec", "out", "init"))
