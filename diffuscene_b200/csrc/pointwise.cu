@@ -8,8 +8,34 @@
 // scene_synthesis/networks/diffusion_ddpm.py (q_sample :276-286, p_sample :339-352, p_losses :520-652).
 #include "kernels.cuh"
 #include <cstdlib>
+#include <utility>
 
 namespace ds {
+
+// Programmatic dependent launch for the pointwise kernels of the step program: launched with the PDL attribute, a
+// kernel may be scheduled while the previous kernel in the stream (a GEMM that issued griddepcontrol.launch_dependents)
+// drains; it touches no memory before `pdl_wait()`.  These kernels do NOT trigger their own dependents early (their
+// dependents are 96-register, 216 KB GEMM CTAs that would crowd out the remaining waves).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 
 static inline int cdiv(int64_t a, int64_t b) { return int((a + b - 1) / b); }
 
@@ -183,6 +209,7 @@ template <typename T, bool EXACT>
 __global__ void __launch_bounds__(256) k_layernorm512(const T* __restrict__ in, int ld_in, T* __restrict__ out,
                                                       int ld_out, const float* __restrict__ g,
                                                       const T* __restrict__ res, int ld_res, int M) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -219,7 +246,7 @@ void launch_layernorm(const T* in, int ld_in, T* out, int ld_out, const float* g
                       int C, cudaStream_t s) {
   constexpr bool EX = sizeof(T) == 4;
   const bool vec_ok = C == 512 && ld_in % 16 == 0 && ld_out % 16 == 0 && (!res || ld_res % 16 == 0);
-  if (vec_ok) k_layernorm512<T, EX><<<cdiv(M, 8), 256, 0, s>>>(in, ld_in, out, ld_out, g, res, ld_res, M);
+  if (vec_ok) launch_pdl(k_layernorm512<T, EX>, dim3(cdiv(M, 8)), dim3(256), 0, s, in, ld_in, out, ld_out, g, res, ld_res, M);
   else k_layernorm<T, EX><<<cdiv(M, 4), 128, 0, s>>>(in, ld_in, out, ld_out, g, res, ld_res, M, C);
 }
 
@@ -480,6 +507,7 @@ __global__ void __launch_bounds__(128) k_linattn_frag(const bf16* __restrict__ q
                                                       int ld_out, int n_scenes, int n_rt) {
   constexpr int MT = NT / 16;         // 16-token tiles
   constexpr int RS = 40;              // shared-memory row stride (bf16): 80 B, conflict-free for ldmatrix
+  pdl_wait();
   const int n = NE > 0 ? NE : n_rt;
   __shared__ __align__(16) bf16 sm_v[4][NT * RS];
   __shared__ __align__(16) bf16 sm_k[4][NT * RS];
@@ -622,10 +650,10 @@ void launch_linattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int 
     const bool vec_ok = (ld % 8 == 0) && (ld_out % 2 == 0) && ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 4 == 0);
     static const bool use_frag = !(getenv("DS_LINATTN_FRAG") && atoi(getenv("DS_LINATTN_FRAG")) == 0);
     if (vec_ok && use_frag && n_obj <= 32) {
-      if (n_obj == 12) k_linattn_frag<16, 12><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
-      else if (n_obj == 21) k_linattn_frag<32, 21><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
-      else if (n_obj <= 16) k_linattn_frag<16, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
-      else k_linattn_frag<32, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      if (n_obj == 12) launch_pdl(k_linattn_frag<16, 12>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj == 21) launch_pdl(k_linattn_frag<32, 21>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj <= 16) launch_pdl(k_linattn_frag<16, 0>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
+      else launch_pdl(k_linattn_frag<32, 0>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
       return;
     }
     if (n_obj <= 16) {
@@ -700,6 +728,7 @@ __global__ void __launch_bounds__(128) k_softattn_frag(const bf16* __restrict__ 
                                                        int ld_out, int n_scenes, int n_rt) {
   constexpr int MT = NT / 16;
   constexpr int RS = 40;
+  pdl_wait();
   const int n = NE > 0 ? NE : n_rt;
   __shared__ __align__(16) bf16 sm_v[4][NT * RS];
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
@@ -812,10 +841,10 @@ void launch_softattn(const T* qkv, int ld, T* out, int ld_out, int n_scenes, int
     const bool vec_ok = (ld % 8 == 0) && (ld_out % 2 == 0) && ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)out % 4 == 0);
     static const bool use_frag = !(getenv("DS_SOFTATTN_FRAG") && atoi(getenv("DS_SOFTATTN_FRAG")) == 0);
     if (vec_ok && use_frag && n_obj <= 32) {
-      if (n_obj == 12) k_softattn_frag<16, 12><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
-      else if (n_obj == 21) k_softattn_frag<32, 21><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
-      else if (n_obj <= 16) k_softattn_frag<16, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
-      else k_softattn_frag<32, 0><<<n_scenes, 128, 0, s>>>(qkv, ld, out, ld_out, n_scenes, n_obj);
+      if (n_obj == 12) launch_pdl(k_softattn_frag<16, 12>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj == 21) launch_pdl(k_softattn_frag<32, 21>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
+      else if (n_obj <= 16) launch_pdl(k_softattn_frag<16, 0>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
+      else launch_pdl(k_softattn_frag<32, 0>, dim3(n_scenes), dim3(128), 0, s, qkv, ld, out, ld_out, n_scenes, n_obj);
       return;
     }
   }

@@ -22,6 +22,7 @@ import torch.nn as nn
 from torch.nn.utils import clip_grad_norm_
 
 from ..engine import DenoiserEngine
+from ..parallel import allreduce_gradients
 from ..schedule import get_betas, make_tables
 from ..stats_logger import StatsLogger
 from ..weights import NetSpec, seeded_tensor, unet1d_param_specs
@@ -444,6 +445,7 @@ def train_on_batch(model, optimizer, sample_params, config):
     optimizer.zero_grad()
     loss, loss_dict = model.get_loss(sample_params)
     loss.backward()
+    allreduce_gradients(model.parameters())       # no-op outside a torch.distributed process group
     grad_norm = clip_grad_norm_(model.parameters(), config["training"]["max_grad_norm"])
     optimizer.step()
     model.mark_weights_dirty()
