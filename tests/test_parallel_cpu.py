@@ -79,7 +79,8 @@ def test_two_rank_gradient_mean_equals_full_batch_gradient():
     model = _make_model()
     g = torch.Generator().manual_seed(11)
     x, y = torch.randn(8, 6, generator=g), torch.randn(8, 4, generator=g)
-    ((model(x) - y) ** 2).mean().backward()
+    with torch.enable_grad():          # other test modules may leave autograd disabled in this process
+        ((model(x) - y) ** 2).mean().backward()
     want = [p.grad for p in model.parameters()]
     for rank, n_coll, grads in res:
         assert n_coll >= 2
