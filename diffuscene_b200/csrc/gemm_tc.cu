@@ -1406,7 +1406,9 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 1; }   // on by default; DS_TC_PDL=0 disables
+  // off by default: with the 576-thread channels-on-lanes kernels in the step program PDL measured 1.5 % SLOWER
+  // (the chip is power-capped; early-resident CTAs polling their barriers cost clock); DS_TC_PDL=1 enables
+  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 0; }
   if (pdl) {      // may start while the previous kernel in the stream drains (it waits at griddepcontrol.wait)
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
@@ -1443,7 +1445,7 @@ static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cuda
   cfg.gridDim = dim3(total < p->num_sms ? total : p->num_sms);
   cudaLaunchAttribute attr[1];
   static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 1; }
+  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 0; }
   if (pdl) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -20,7 +20,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 1; }
+  if (pdl < 0) { const char* e = getenv("DS_PW_PDL"); pdl = e ? atoi(e) : 0; }     // off by default (see gemm_tc.cu)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
