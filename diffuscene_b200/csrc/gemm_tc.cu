@@ -1,5 +1,8 @@
-// tcgen05 tensor-core GEMM for sm_100a:  D[M,N] = act([A0|A1][M,K] * W[N,K]^T + bias) (+ residual)
-// bf16 operands, fp32 accumulation in TMEM, bf16 output.
+// tcgen05 tensor-core GEMMs for sm_100a:  D[M,N] = act([A0|A1][M,K] * W[N,K]^T + bias) (+ residual)
+// bf16 operands, fp32 accumulation in TMEM, bf16 output.  Two kernels share the TMA / mbarrier / TMEM plumbing:
+//   k_gemm_tc<BN, GN>   rows of D on the TMEM lanes (activations = M operand), described right below;
+//   k_gemm_gnt<NOBJ>    output CHANNELS on the TMEM lanes (weights = M operand, whole scenes = N operand), the
+//                       kernel of the fused conv + GroupNorm + FiLM + SiLU blocks -- see its own header further down.
 //
 // This kernel carries every 1x1-conv / linear layer of the denoiser in throughput mode (reference:
 // F.conv1d / nn.Linear calls of scene_synthesis/networks/denoise_net.py:91,183,214-217,244-245,487-502).
