@@ -767,8 +767,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 // GroupNorm statistics: per-(scene, channel) partials -> shared memory -> 8 threads per (scene, group) reduce.
 template <int NOBJ>
 struct GntCfg {
-  static constexpr int SC = (NOBJ == 12) ? 16 : 256 / NOBJ;   // scenes per tile
-  static constexpr int TOK = SC * NOBJ;                         // tokens per tile (192)
+  static constexpr int SC = (NOBJ == 12) ? 16 : 256 / NOBJ;   // scenes per tile (16 for N = 12, 12 for N = 21)
+  static constexpr int TOK = SC * NOBJ;                         // tokens per tile (192 / 252)
   static constexpr int UN = (TOK + 15) / 16 * 16;               // UMMA N = TMA box rows of the activation tile
   static constexpr int EPI_W = 16;                              // epilogue warps: 4 per TMEM lane quadrant
   static constexpr int NP = EPI_W / 4;                          // each quadrant's warps split the scenes NP ways
@@ -776,14 +776,21 @@ struct GntCfg {
   static constexpr int THREADS = 64 + EPI_W * 32;
   static constexpr int B_BYTES = UN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = (UN <= 192) ? 4 : 3;
   static constexpr int ACC_STRIDE = 256;                        // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 512;
   static constexpr int CHAN_MAX_N = 512;
   static constexpr int CHAN_BYTES = CHAN_MAX_N * 20;            // bias | (gamma, beta) | uniform FiLM
   static constexpr int RED_BYTES = SC * 128 * 8;                // (sum, sum of squares) per (scene, channel)
   static constexpr int STAT_BYTES = SC * 2 * 8;                 // (mean, rstd) per (scene, group of the tile)
-  static constexpr int STG_ROWS = 16;                           // ldmatrix addresses up to token 15 stay inside the block
+  // a scene is moved as NPAIR (token 2i, token 2i + 1) pairs; an odd scene pads its last pair with a dummy token
+  static constexpr int NPAIR = (NOBJ + 1) / 2;
+  static constexpr int NG4 = NPAIR / 4;                         // full ldmatrix / stmatrix .x4 groups (8 tokens each)
+  static constexpr int REM = NPAIR % 4;                         // 0, 2 (-> .x2) or 3 (-> .x4 with a zero pair)
+  static constexpr int PKN = 4 * NG4 + (REM == 0 ? 0 : (REM <= 2 ? 2 : 4));
+  static constexpr int PIECES = NOBJ * 4;                       // 16-byte pieces of a [token][32 channel] block
+  static constexpr int PROUNDS = (PIECES + 31) / 32;
+  static constexpr int STG_ROWS = 8 * (NG4 + 1);                // ldmatrix row addresses stay inside the block
   static constexpr int STG_BYTES = STG_ROWS * 64;               // one [token][32 channel] bf16 block
   static constexpr int SCRATCH_OFF = STAGES * STAGE_BYTES + 256;
   static constexpr int RED_OFF = SCRATCH_OFF + CHAN_BYTES;
@@ -793,7 +800,9 @@ struct GntCfg {
   static_assert(SC % NP == 0, "scenes must split evenly over the warps of a quadrant");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must stay swizzle-atom aligned");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
-  static_assert(NOBJ % 2 == 0 && NOBJ == 12, "token pairs must not straddle scenes (only N = 12 is instantiated)");
+  static_assert(NOBJ == 12 || NOBJ == 21, "TMEM load shapes are written out for N = 12 and N = 21");
+  static_assert(REM != 1, "a single trailing pair would need an .x1 matrix");
+  static_assert(UN <= 256 && 2 * UN <= TMEM_COLS + (ACC_STRIDE - UN), "accumulators must fit TMEM");
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(UN >> 3) << 17) |
                                     (uint32_t(BM >> 4) << 24);
 };
@@ -808,6 +817,26 @@ __device__ __forceinline__ void tmem_ld12_issue(uint32_t taddr, uint32_t (&r)[12
                : "r"(taddr + 8u)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld21_issue(uint32_t taddr, uint32_t (&r)[21]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
+               : "r"(taddr + 16u)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[20]) : "r"(taddr + 20u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld21_wait(uint32_t (&r)[21]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20])
+               :
+               : "memory");
+}
 // wait for the loads above; the registers are listed as read-write so that the compiler cannot move or copy
 // them between the (asynchronous) issue and this point
 __device__ __forceinline__ void tmem_ld12_wait(uint32_t (&r)[12]) {
@@ -817,6 +846,11 @@ __device__ __forceinline__ void tmem_ld12_wait(uint32_t (&r)[12]) {
                :
                : "memory");
 }
+// one scene's columns of the accumulator (N consecutive TMEM columns) -> N registers
+__device__ __forceinline__ void tmem_ld_scene_issue(uint32_t taddr, uint32_t (&r)[12]) { tmem_ld12_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ld_scene_issue(uint32_t taddr, uint32_t (&r)[21]) { tmem_ld21_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ld_scene_wait(uint32_t (&r)[12]) { tmem_ld12_wait(r); }
+__device__ __forceinline__ void tmem_ld_scene_wait(uint32_t (&r)[21]) { tmem_ld21_wait(r); }
 __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
@@ -1005,7 +1039,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     };
     // coalesced view of a staging block: 16-byte piece `lane` and (for 12 tokens) `lane + 32` of its 48 pieces
     const int cr0 = lane >> 2, cp0 = lane & 3;
-    const bool second = lane < NOBJ * 4 - 32;
+    constexpr bool OBJ_IN_REGS = NOBJ <= 12;         // per-object FiLM pairs of a channel held in registers
     const int s_begin = part * Cfg::SPP;
     // tile walk without divisions: (ct, tt) advance by a constant step with carry
     const int step_cg = unit_step % cgn, step_tt = unit_step / cgn;
@@ -1039,8 +1073,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           P = 0.5f * gb.x * fu.x;
           Q = 0.5f * fmaf(gb.y, fu.x, fu.y);
         }
-        float Fo[FM == 1 ? NOBJ : 1], Go[FM == 1 ? NOBJ : 1];     // per-object FiLM of this channel
-        if constexpr (FM == 1) {
+        float Fo[(FM == 1 && OBJ_IN_REGS) ? NOBJ : 1], Go[(FM == 1 && OBJ_IN_REGS) ? NOBJ : 1];   // per-object FiLM
+        if constexpr (FM == 1 && OBJ_IN_REGS) {
 #pragma unroll
           for (int j = 0; j < NOBJ; ++j) {
             const float* fr = epi.film.base + (int64_t)j * epi.film.row_stride + ch;
@@ -1051,18 +1085,22 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         const int scene0 = tt * Cfg::SC + s_begin;                 // first scene of this warp in this tile
         const int n_live = n_scenes_total - scene0;                // scenes si < n_live exist
         const int col0 = ct * BM + 32 * q + cp0 * 8;
-        // piece pointers of scene 0 (rows cr0 and cr0 + 8 of the [token][32 channel] block); + NOBJ rows per scene
+        // piece pointers of scene 0 (rows cr0 + 8 r of the [token][32 channel] block, r = 0..PROUNDS-1); + NOBJ rows per scene
         bf16* dp = epi.d + ((int64_t)scene0 * NOBJ + cr0) * epi.ldd + col0;
         const bf16* rp = RES ? epi.res + ((int64_t)scene0 * NOBJ + cr0) * epi.ldres + col0 : nullptr;
         const int64_t d_step = (int64_t)NOBJ * epi.ldd, r_step = (int64_t)NOBJ * epi.ldres;
         const int64_t d_hi = (int64_t)8 * epi.ldd, r_hi = (int64_t)8 * epi.ldres;
         // residual: software-pipelined one scene ahead; the first fetch is issued before the accumulator is complete
-        uint4 rg0 = make_uint4(0u, 0u, 0u, 0u), rg1 = rg0;
+        uint4 rg[Cfg::PROUNDS];
+#pragma unroll
+        for (int r = 0; r < Cfg::PROUNDS; ++r) rg[r] = make_uint4(0u, 0u, 0u, 0u);
+        auto fetch_res = [&]() {
+#pragma unroll
+          for (int r = 0; r < Cfg::PROUNDS; ++r)
+            if (lane + 32 * r < Cfg::PIECES) rg[r] = __ldg(reinterpret_cast<const uint4*>(rp + r * r_hi));
+        };
         if constexpr (RES) {
-          if (0 < n_live) {
-            rg0 = __ldg(reinterpret_cast<const uint4*>(rp));
-            if (second) rg1 = __ldg(reinterpret_cast<const uint4*>(rp + r_hi));
-          }
+          if (0 < n_live) fetch_res();
         }
         unsigned long long t0 = epi.trace ? clock64() : 0;
         mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
@@ -1072,16 +1110,16 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
 
         // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
         if constexpr (FM != 4) {
-          uint32_t va[12];
-          tmem_ld12_issue(taddr, va);
+          uint32_t va[NOBJ];
+          tmem_ld_scene_issue(taddr, va);
           float2* rdst = red + s_begin * 128 + 32 * q + lane;
 #pragma unroll
           for (int si = 0; si < Cfg::SPP; ++si) {
-            tmem_ld12_wait(va);
+            tmem_ld_scene_wait(va);
             float v[NOBJ];
 #pragma unroll
             for (int j = 0; j < NOBJ; ++j) v[j] = __uint_as_float(va[j]);
-            if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((si + 1) * NOBJ), va);
+            if (si + 1 < Cfg::SPP) tmem_ld_scene_issue(taddr + uint32_t((si + 1) * NOBJ), va);
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int j = 0; j < NOBJ; ++j) {
@@ -1119,8 +1157,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         if constexpr (FM != 4) epi_bar();
 
         // ---- pass 2: normalise + FiLM + SiLU (+ residual) per scene, transposed store through the staging blocks
-        uint32_t va[12];
-        tmem_ld12_issue(taddr, va);
+        uint32_t va[NOBJ];
+        tmem_ld_scene_issue(taddr, va);
         const float2* stp = stat + s_begin * 2 + gq;
 #pragma unroll 1
         for (int si = 0; si < Cfg::SPP; ++si) {
@@ -1140,19 +1178,29 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             a = st.y * Ps;
             b = fmaf(bias - st.x, a, Qs);
           }
-          tmem_ld12_wait(va);
-          float y[NOBJ];
+          tmem_ld_scene_wait(va);
+          float y[2 * Cfg::PKN];                      // tokens >= NOBJ: padding of the last pair(s), never stored
+#pragma unroll
+          for (int j = NOBJ; j < 2 * Cfg::PKN; ++j) y[j] = 0.f;
 #pragma unroll
           for (int j = 0; j < NOBJ; ++j) y[j] = FM == 4 ? __uint_as_float(va[j]) + b : fmaf(__uint_as_float(va[j]), a, b);
-          if (si + 1 < Cfg::SPP) tmem_ld12_issue(taddr + uint32_t((si + 1) * NOBJ), va);
+          if (si + 1 < Cfg::SPP) tmem_ld_scene_issue(taddr + uint32_t((si + 1) * NOBJ), va);
           else {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(ab));          // accumulator drained: the next tile's MMAs may start
           }
           if constexpr (FM == 1) {
+            if constexpr (OBJ_IN_REGS) {
 #pragma unroll
-            for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(y[j], Fo[j], Go[j]);
+              for (int j = 0; j < NOBJ; ++j) y[j] = fmaf(y[j], Fo[j], Go[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < NOBJ; ++j) {
+                const float* fr = epi.film.base + (int64_t)j * epi.film.row_stride + ch;
+                y[j] = 0.5f * fmaf(y[j], __ldg(fr) + 1.0f, __ldg(fr + epi.C));
+              }
+            }
           }
           if constexpr (FM == 2) {
             if (live) {
@@ -1176,40 +1224,56 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             for (int j = 0; j < NOBJ; ++j) y[j] = silu_from_half(y[j]);
           }
           if constexpr (RES) {
-            sts128(stg_in + uint32_t(lane * 16), rg0);
-            if (second) sts128(stg_in + uint32_t((lane + 32) * 16), rg1);
-            rp += r_step;
-            if (si + 1 < Cfg::SPP && si + 1 < n_live) {          // next scene's rows land while this one is finished
-              rg0 = __ldg(reinterpret_cast<const uint4*>(rp));
-              if (second) rg1 = __ldg(reinterpret_cast<const uint4*>(rp + r_hi));
-            }
-            __syncwarp();
-            uint32_t r4[4], r2[2];
-            ldsm_x4_t(r4, stg_in + mrow);
-            ldsm_x2_t(r2, stg_in + 512u + mrow);        // lanes 0-15 address tokens 8..11
-            const uint32_t rr[6] = {r4[0], r4[1], r4[2], r4[3], r2[0], r2[1]};
 #pragma unroll
-            for (int i = 0; i < NOBJ / 2; ++i) {
+            for (int r = 0; r < Cfg::PROUNDS; ++r)
+              if (lane + 32 * r < Cfg::PIECES) sts128(stg_in + uint32_t((lane + 32 * r) * 16), rg[r]);
+            rp += r_step;
+            if (si + 1 < Cfg::SPP && si + 1 < n_live) fetch_res();       // next scene's rows land while this one is finished
+            __syncwarp();
+            uint32_t rr[Cfg::PKN];
+#pragma unroll
+            for (int g8 = 0; g8 < Cfg::NG4; ++g8) {
+              uint32_t r4[4];
+              ldsm_x4_t(r4, stg_in + uint32_t(g8 * 512) + mrow);
+              rr[4 * g8] = r4[0]; rr[4 * g8 + 1] = r4[1]; rr[4 * g8 + 2] = r4[2]; rr[4 * g8 + 3] = r4[3];
+            }
+            if constexpr (Cfg::REM == 2) {
+              uint32_t r2[2];
+              ldsm_x2_t(r2, stg_in + uint32_t(Cfg::NG4 * 512) + mrow);      // lanes 0-15 address the 4 trailing tokens
+              rr[4 * Cfg::NG4] = r2[0]; rr[4 * Cfg::NG4 + 1] = r2[1];
+            } else if constexpr (Cfg::REM == 3) {
+              uint32_t r4[4];
+              ldsm_x4_t(r4, stg_in + uint32_t(Cfg::NG4 * 512) + mrow);
+              rr[4 * Cfg::NG4] = r4[0]; rr[4 * Cfg::NG4 + 1] = r4[1]; rr[4 * Cfg::NG4 + 2] = r4[2]; rr[4 * Cfg::NG4 + 3] = r4[3];
+            }
+#pragma unroll
+            for (int i = 0; i < Cfg::NPAIR; ++i) {
               y[2 * i] += __uint_as_float(rr[i] << 16);
               y[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
             }
           }
-          uint32_t pk[NOBJ / 2];
+          uint32_t pk[Cfg::PKN];
 #pragma unroll
-          for (int i = 0; i < NOBJ / 2; ++i) {
+          for (int i = 0; i < Cfg::PKN; ++i) {
             __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
             pk[i] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          stsm_x4_t(stg_out + mrow, pk[0], pk[1], pk[2], pk[3]);
-          stsm_x2_t(stg_out + 512u + mrow, pk[4], pk[5]);
+#pragma unroll
+          for (int g8 = 0; g8 < Cfg::NG4; ++g8)
+            stsm_x4_t(stg_out + uint32_t(g8 * 512) + mrow, pk[4 * g8], pk[4 * g8 + 1], pk[4 * g8 + 2], pk[4 * g8 + 3]);
+          if constexpr (Cfg::REM == 2)
+            stsm_x2_t(stg_out + uint32_t(Cfg::NG4 * 512) + mrow, pk[4 * Cfg::NG4], pk[4 * Cfg::NG4 + 1]);
+          else if constexpr (Cfg::REM == 3)
+            stsm_x4_t(stg_out + uint32_t(Cfg::NG4 * 512) + mrow, pk[4 * Cfg::NG4], pk[4 * Cfg::NG4 + 1], pk[4 * Cfg::NG4 + 2],
+                      pk[4 * Cfg::NG4 + 3]);
           __syncwarp();
           if (live) {
-            const uint4 o0 = lds128(stg_out + uint32_t(lane * 16));
-            *reinterpret_cast<uint4*>(dp) = o0;
-            if (second) {
-              const uint4 o1 = lds128(stg_out + uint32_t((lane + 32) * 16));
-              *reinterpret_cast<uint4*>(dp + d_hi) = o1;
-            }
+#pragma unroll
+            for (int r = 0; r < Cfg::PROUNDS; ++r)
+              if (lane + 32 * r < Cfg::PIECES) {
+                const uint4 o = lds128(stg_out + uint32_t((lane + 32 * r) * 16));
+                *reinterpret_cast<uint4*>(dp + r * d_hi) = o;
+              }
           }
           dp += d_step;
           __syncwarp();
@@ -1304,6 +1368,7 @@ bool tc_runtime_available(char* err, int err_len) {
   cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
   return true;
 }
@@ -1344,11 +1409,11 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   const bool gn = g.gn != 0 && !plain_t;
   const bool gnt = g.gn == 2 || plain_t;
   if (g.gn == 2 && !tc_gnt_supported(g.n_obj, g.N)) {
-    if (err) snprintf(err, err_len, "channels-on-lanes GroupNorm GEMM needs n_obj == 12 and N %% 128 == 0, N <= 512");
+    if (err) snprintf(err, err_len, "channels-on-lanes GroupNorm GEMM needs n_obj in {12, 21} and N %% 128 == 0, N <= 512");
     return nullptr;
   }
   if (plain_t && !tc_gnt_plain_supported(g.n_obj, g.N)) {
-    if (err) snprintf(err, err_len, "channels-on-lanes GEMM needs n_obj == 12 and N %% 128 == 0");
+    if (err) snprintf(err, err_len, "channels-on-lanes GEMM needs n_obj in {12, 21} and N %% 128 == 0");
     return nullptr;
   }
   if (gn && (g.N % 256 || g.N > TcCfg<256, true>::CHAN_MAX_N || g.n_obj < 1 || g.n_obj > 128 || !g.gamma || !g.beta)) {
@@ -1372,7 +1437,8 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     if (const char* e = getenv("DS_GNT_CLUSTER")) gnt_cs = atoi(e);
     if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
   }
-  const uint32_t act_box = gnt ? uint32_t(GntCfg<12>::UN / gnt_cs) : uint32_t(BM);     // rows of one activation load
+  const int gnt_un = g.n_obj == 21 ? GntCfg<21>::UN : GntCfg<12>::UN, gnt_tok = g.n_obj == 21 ? GntCfg<21>::TOK : GntCfg<12>::TOK;
+  const uint32_t act_box = gnt ? uint32_t(gnt_un / gnt_cs) : uint32_t(BM);     // rows of one activation load
   bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, act_box, err, err_len);
   if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, act_box, err, err_len);
   if (ok && !g.a1) p->tm_a1 = p->tm_a0;
@@ -1381,7 +1447,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) p->cluster = 1;
   if (gnt) p->cluster = gnt_cs;
   if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, gnt ? BM : p->bn / p->cluster, err, err_len);
-  const int tile_rows = gnt ? GntCfg<12>::TOK : (gn ? (BM / g.n_obj) * g.n_obj : BM);
+  const int tile_rows = gnt ? gnt_tok : (gn ? (BM / g.n_obj) * g.n_obj : BM);
   if (gn && !gnt && tile_rows / g.n_obj > TcCfg<256, true>::SPT_FAST) {
     if (err) snprintf(err, err_len, "fused GroupNorm epilogue supports at most %d scenes per 128-row tile (n_obj=%d)",
                       TcCfg<256, true>::SPT_FAST, g.n_obj);
@@ -1460,12 +1526,18 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
 }
 
-bool tc_gnt_plain_supported(int n_obj, int N) { return n_obj == 12 && N % BM == 0; }
-bool tc_gnt_supported(int n_obj, int N) { return n_obj == 12 && N % BM == 0 && N <= GntCfg<12>::CHAN_MAX_N; }
+// object counts the channels-on-lanes kernel is instantiated for (DS_GNT21=0 keeps N = 21 on the row-major kernel)
+static bool gnt_nobj_ok(int n_obj) {
+  static const int allow21 = getenv("DS_GNT21") ? atoi(getenv("DS_GNT21")) : 1;
+  return n_obj == 12 || (n_obj == 21 && allow21);
+}
+bool tc_gnt_plain_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0; }
+bool tc_gnt_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0 && N <= GntCfg<12>::CHAN_MAX_N; }
 
+template <int NOBJ>
 static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cudaStream_t s) {
-  using Cfg = GntCfg<12>;
-  const int n_scenes = epi.M / 12;
+  using Cfg = GntCfg<NOBJ>;
+  const int n_scenes = epi.M / NOBJ;
   const int cs = p->cluster;
   const int total = ((n_scenes + Cfg::SC - 1) / Cfg::SC) * (epi.N / BM / cs);      // work units per cluster
   if (total == 0) return 0;
@@ -1495,14 +1567,14 @@ static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cuda
       cfg.numAttrs = na;
       cfg.gridDim = dim3(max_cl * cs);
       int n = 0;
-      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<12>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
+      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<NOBJ>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
     }
     if (cached < max_cl) max_cl = cached;
   }
   cfg.attrs = na ? attr : nullptr;
   cfg.numAttrs = na;
   cfg.gridDim = dim3((total < max_cl ? total : max_cl) * cs);
-  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<12>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<NOBJ>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
 }
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
@@ -1511,7 +1583,7 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   if (p->gnt) {
     int* fd = nullptr;
     cudaHostGetDevicePointer((void**)&fd, g_err_flag, 0);
-    return launch_gnt(p, epi, fd, s);
+    return epi.n_obj == 21 ? launch_gnt<21>(p, epi, fd, s) : launch_gnt<12>(p, epi, fd, s);
   }
   const int num_m = (M + epi.tile_rows - 1) / epi.tile_rows;
   const int total_ct = ((num_m + p->cluster - 1) / p->cluster) * (epi.N / p->bn);

@@ -157,7 +157,9 @@ def test_batch_independence_at_full_size():
 
 
 def test_batch_independence_living_room_shape():
-    """N = 21 objects: 126-row tiles (6 scenes), 21-entry per-object FiLM table, x0-prediction, fixedlarge variance."""
+    """N = 21 objects (odd scenes): the default fuse level runs k_gemm_gnt<21> (12 scenes = 252 tokens per tile, 11
+    token pairs per scene with a padded last pair, per-object FiLM loaded per element); x0-prediction, fixedlarge
+    variance."""
     eng, case, spec, inp = get_engine("liv65", "bf16", "tcgen05")
     B = 1500
     g = torch.Generator(device="cpu").manual_seed(9)
