@@ -33,7 +33,7 @@ static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+  (void)cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);   // errors surface at the caller's sync / cudaGetLastError
 }
 
 

@@ -192,7 +192,10 @@ DS_API int ds_test_gemm_bf16(int backend, const void* a_dev, const void* w_dev, 
                       int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
 
 /* Bring-up / profiling aid: one tcgen05 GEMM (GroupNorm epilogue when n_obj > 0) timed with CUDA events over
- * `reps` launches, plus per-role cycle counters of one traced launch: trace_host[256][8] uint64. */
+ * `reps` launches, plus per-role cycle counters of one traced launch: trace_host[256][8] uint64.
+ * n_obj < 0 selects the channels-on-lanes kernel for |n_obj| objects per scene; the caller then passes the weight
+ * rows in that kernel's order (stored row 32b+l = channel 32b + 8(l%4) + l/4).  With gamma_dev == NULL it runs as a
+ * plain GEMM whose activation (0 none, 1 GELU, 2 SiLU) travels in bits 8.. of `reps`. */
 DS_API int ds_test_gemm_trace(const void* a_dev, const void* w_dev, const float* bias_dev, const void* res_dev,
                               void* d_dev, int32_t M, int32_t N, int32_t K, int32_t n_obj, const float* gamma_dev,
                               const float* beta_dev, int32_t reps, unsigned long long* trace_host, float* usec);
