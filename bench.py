@@ -27,6 +27,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 F_SCENE_MFLOP = {"bedroom": 870.3, "living": 1455.7}       # forward FLOPs / scene / step
+# the two bedroom shapes SURVEY 8(d) / BASELINE.md 3 name: the reference's real one (d = 62, the default) and
+# BASELINE.json's synthetic one (d = 97: angle_dim 4, class_dim 23, objfeat_dim 64; 871.2 MFLOP / scene / step)
+SHAPES = {"real62": (dict(), 62, 870.3),
+          "synth97": (dict(channels=97, class_dim=23, angle_dim=4, objfeat_dim=64), 97, 871.2)}
+
+
+def bed_kwargs(shape):
+    kw = dict(BED)
+    kw.update(SHAPES[shape][0])
+    return kw
 BED = dict(dim=512, dim_mults=[1, 1, 1, 1], channels=62, objectness_dim=0, class_dim=22, angle_dim=2,
            objfeat_dim=32, context_dim=0, instanclass_dim=128, seperate_all=True)
 
@@ -76,7 +86,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_scenes_per_sec(batch: int, steps: int, threads: int):
+def oracle_scenes_per_sec(batch: int, steps: int, threads: int, shape="real62"):
     """CPU baseline: the oracle restatement of the reference path (fp32 torch on the host cores), timed on
     a bounded sample (`steps` diffusion steps of `batch` scenes) and scaled to a 1000-step sample."""
     from diffuscene_b200.weights import NetSpec, seeded_state_dict, unet1d_param_specs
@@ -84,11 +94,11 @@ def oracle_scenes_per_sec(batch: int, steps: int, threads: int):
     from oracle.unet1d_ref import unet1d_forward
     torch.set_num_threads(threads)
     torch.set_grad_enabled(False)
-    spec = NetSpec.from_net_kwargs(BED)
+    spec = NetSpec.from_net_kwargs(bed_kwargs(shape))
     sd = seeded_state_dict(unet1d_param_specs(spec), seed=0)
     sched = D.make_schedule(D.make_betas("linear", 1e-4, 0.02, 1000), "v", "fixedsmall")
     ctx = torch.randn(12, 128)[None].expand(batch, 12, 128).contiguous()
-    x = torch.randn(batch, 12, 62)
+    x = torch.randn(batch, 12, SHAPES[shape][1])
     den = lambda xx, tt: unet1d_forward(sd, spec, xx, tt, ctx, None)
     t0 = None
     for i, step in enumerate(reversed(range(1000 - steps - 1, 1000))):
@@ -110,7 +120,7 @@ def run_reference(args):
     batch, dsteps = 32, 2
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt = oracle_scenes_per_sec(batch, dsteps, threads)
+        v, dt = oracle_scenes_per_sec(batch, dsteps, threads, args.shape)
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
@@ -119,7 +129,7 @@ def run_reference(args):
         "impl": "reference", "metric": "scenes/sec full 1000-step DDPM sample", "value": v, "unit": "scenes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * batch / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "uncond bedroom N=12 d=62 T=1000 DDPM sampling (BASELINE configs[1])"},
+        "config": {"workload": "uncond bedroom N=12 d=%d T=1000 DDPM sampling (BASELINE configs[1])" % SHAPES[args.shape][1]},
         "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -137,6 +147,8 @@ def main():
     ap.add_argument("--backend", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="scenes per L2-resident sub-batch (0: whole batch at once)")
+    ap.add_argument("--shape", default="real62", choices=sorted(SHAPES), help="bedroom attribute layout: the reference's "
+                    "real config (d=62) or BASELINE.json's synthetic d=97")
     ap.add_argument("--fuse", type=int, default=None, help="fuse_level override (1: row-major fused GroupNorm GEMM, "
                                                             "2: channels-on-lanes variant); default: the engine's")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device time table to stderr")
@@ -157,7 +169,8 @@ def main():
     from diffuscene_b200.schedule import get_betas, make_tables
     from diffuscene_b200.weights import NetSpec, seeded_state_dict, unet1d_param_specs
 
-    spec = NetSpec.from_net_kwargs(BED)
+    spec = NetSpec.from_net_kwargs(bed_kwargs(args.shape))
+    D_ATTR, F_SCENE = SHAPES[args.shape][1], SHAPES[args.shape][2]
     N_OBJ, T, B = 12, args.timesteps, args.batch
     eng = DenoiserEngine(spec, N_OBJ, T, precision=args.precision, gemm_backend=args.backend, device=local,
                          fuse_level=args.fuse)
@@ -165,7 +178,7 @@ def main():
     eng.set_schedule(make_tables(get_betas("linear", 1e-4, 0.02, T), "v", "fixedsmall"))
     g = torch.Generator().manual_seed(1)
     pos_emb = torch.randn(N_OBJ, 128, generator=g).pin_memory()                      # positional_embedding
-    x_T_host = torch.randn(B, N_OBJ, 62, generator=g).pin_memory()
+    x_T_host = torch.randn(B, N_OBJ, D_ATTR, generator=g).pin_memory()
     eng.set_context(pos_emb.to(dev), shared=True)
     x_T_dev = x_T_host.to(dev)
 
@@ -216,15 +229,15 @@ def main():
         ms_per_step = ms / args.steps
         us_per_dstep = ms_per_step * 1000.0 / T
         peak_tf, peak_gbs, which = measured_peaks()
-        flops_per_launch = B * F_SCENE_MFLOP["bedroom"] * 1e6            # one diffusion step of one GPU's batch
+        flops_per_launch = B * F_SCENE * 1e6            # one diffusion step of one GPU's batch
         achieved_tf = flops_per_launch / (us_per_dstep * 1e-6) / 1e12
         res = {
             "metric": "scenes/sec full 1000-step DDPM sample", "value": value, "unit": "scenes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "uncond bedroom N=12 d=62 T=%d DDPM sampling, batch=%d scenes/GPU "
-                                   "(BASELINE configs[1]), random-init weights" % (T, B),
+            "config": {"workload": "uncond bedroom N=12 d=%d T=%d DDPM sampling, batch=%d scenes/GPU "
+                                   "(BASELINE configs[1]), random-init weights" % (D_ATTR, T, B),
                        "scenes_per_gpu": B, "global_batch": total_scenes, "parallelism": "scene-shard x%d" % world,
                        "l2": "per-step working set (>=20 x 50 MB activation buffers + 63 MB weights) exceeds the "
                              "126 MB L2; no explicit flush"},
@@ -232,11 +245,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": int(x_T_host.numel() * 4 + pos_emb.numel() * 4),
-                    "d2h_bytes_per_step": int(B * N_OBJ * 62 * 4)},
+                    "d2h_bytes_per_step": int(B * N_OBJ * D_ATTR * 4)},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": which + " bf16 sustained",
                          "launch": "one diffusion step (CUDA graph of the step program) over %d scenes; "
-                                   "algorithmic 870.3 MFLOP/scene/step" % B},
+                                   "algorithmic %.1f MFLOP/scene/step" % (B, F_SCENE)},
         }
         # dominant kernel: k_gemm_gnt<12>, the channels-on-lanes tcgen05 GEMM that carries the 56 fused conv + GroupNorm
         # + FiLM + SiLU blocks and the epilogue-bound plain GEMMs (to_qkv, to_out) -- 76 of the 125 launches of a step.
@@ -265,7 +278,7 @@ def main():
                 "frac": dom_flop / (dom_us * 1e-6) / 1e12 / peak_tf,
                 "share_of_step": dom_us / max(1e-9, sum(u for _, u in ops))}
         tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "round1_v8_dram_traffic.json")
-        if B == 4096 and args.precision == "bf16" and eng.fuse_level >= 3 and os.path.exists(tpath):
+        if B == 4096 and args.precision == "bf16" and eng.fuse_level >= 3 and args.shape == "real62" and os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
             res["roofline"]["traffic"] = tj["step_dram_bytes"]
@@ -283,7 +296,7 @@ def main():
                 sys.stderr.write("  %-40s %8.1f\n" % (n, u))
         if not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 32)
-            v, dt = oracle_scenes_per_sec(16, 3, threads)
+            v, dt = oracle_scenes_per_sec(16, 3, threads, args.shape)
             res["cpu_baseline"] = {"value": v, "unit": "scenes/s", "cores": threads, "kind": "port",
                                    "sample": "3 diffusion steps x 16 scenes (oracle, fp32 torch CPU), scaled to 1000 steps"}
         print(json.dumps(res))
