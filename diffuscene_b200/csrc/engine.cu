@@ -1049,6 +1049,7 @@ extern "C" int ds_read_tap(ds_handle* h, const char* name, float* host_out, int6
 }
 
 extern "C" int64_t ds_launch_count(ds_handle* h) { return h ? h->launches : 0; }
+extern "C" int32_t ds_gnt_weight_row(int32_t stored_row) { return tc_gnt_row(stored_row); }
 
 extern "C" int ds_profile_ops(ds_handle* h, int32_t batch, char* names_buf, int64_t names_len, float* usec,
                               int32_t cap) {
