@@ -56,7 +56,7 @@ struct ds_handle {
   std::vector<size_t> v_off;
   // fp32 conditioning path
   float *time_w1 = nullptr, *time_b1 = nullptr, *time_w3 = nullptr, *time_b3 = nullptr, *time_wall = nullptr,
-        *time_ball = nullptr, *time_table = nullptr;
+        *time_ball = nullptr, *time_table = nullptr, *sin_freq = nullptr;
   float *ctx_wall = nullptr, *ctx_ball = nullptr, *ctx_table = nullptr;
   int ctx_rows = 0, ctx_batch = 0;
   bool ctx_shared = false, ctx_set = false;
@@ -313,7 +313,13 @@ static int build_time_table(ds_handle* h) {
   CK(cudaMalloc(&h2, (size_t)T * 4 * C * 4));
   if (h->time_table) cudaFree(h->time_table);
   CK(cudaMalloc(&h->time_table, (size_t)T * ntb * 2 * C * 4));
-  launch_sinusoid(emb, T, C, s);
+  {      // per-handle frequency vector (handles on different devices never share device memory)
+    std::vector<float> hf(C / 2);
+    sinusoid_freqs_host(C, hf.data());
+    int rc = upload_f32(&h->sin_freq, hf.data(), hf.size());
+    if (rc) return rc;
+  }
+  launch_sinusoid(emb, h->sin_freq, T, C, s);
   GemmArgs g;
   memset(&g, 0, sizeof g);
   g.a0 = emb; g.lda0 = C; g.k0 = C; g.w = h->time_w1; g.ldw = C; g.bias = h->time_b1; g.d = h1; g.ldd = 4 * C;
@@ -523,7 +529,7 @@ extern "C" int ds_destroy(ds_handle* h) {
   free_buffers(h);
   cudaFree(h->warena); cudaFree(h->varena);
   cudaFree(h->time_w1); cudaFree(h->time_b1); cudaFree(h->time_w3); cudaFree(h->time_b3);
-  cudaFree(h->time_wall); cudaFree(h->time_ball); cudaFree(h->time_table);
+  cudaFree(h->time_wall); cudaFree(h->time_ball); cudaFree(h->time_table); cudaFree(h->sin_freq);
   cudaFree(h->ctx_wall); cudaFree(h->ctx_ball); cudaFree(h->ctx_table);
   for (float* p : h->kv_w) cudaFree(p);
   cudaFree(h->xctx);
@@ -976,6 +982,29 @@ extern "C" int ds_p_losses(ds_handle* h, const float* x0_dev, const int64_t* t_d
                            h->loss_parts, batch, s);
   launch_loss_dict_mean(h->loss_parts, loss_dict_dev, batch, s);
   h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-processing: object retrieval (stateless; any sm_100 device)
+// ------------------------------------------------------------------------------------------------
+extern "C" int ds_retrieve_objects(const int32_t* class_start_dev, int32_t n_classes, const float* cat_feat_dev,
+                                   const float* cat_size_dev, int32_t feat_dim, int32_t size_dim,
+                                   const int64_t* q_label_dev, const float* q_feat_dev, const float* q_size_dev,
+                                   int32_t num_queries, int32_t mode, int64_t* out_index_dev, void* stream) {
+  if (!class_start_dev || !q_label_dev || !out_index_dev || n_classes <= 0 || num_queries < 0 || mode < 0 || mode > 2)
+    return fail(DS_ERR_INVALID, "bad argument to ds_retrieve_objects");
+  if (mode != 2 && (!cat_feat_dev || !q_feat_dev || feat_dim <= 0)) return fail(DS_ERR_INVALID, "feature arrays needed");
+  if (mode != 1 && (!cat_size_dev || !q_size_dev || size_dim <= 0)) return fail(DS_ERR_INVALID, "size arrays needed");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(DS_ERR_NO_DEVICE, "no CUDA device: diffuscene_b200 has no CPU fallback");
+  }
+  if (num_queries == 0) return 0;
+  launch_retrieve(class_start_dev, n_classes, cat_feat_dev, cat_size_dev, feat_dim, size_dim, q_label_dev, q_feat_dev,
+                  q_size_dev, num_queries, mode, out_index_dev, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return 0;
 }

@@ -40,7 +40,9 @@ void launch_xattn_apply(const T* q, int ldq, const float* ctx, T* out, int ld_ou
                         cudaStream_t s);
 void launch_xattn_prepare(const float* kv, int ld_kv, float* ctx, int n_scenes, int L, cudaStream_t s);
 
-void launch_sinusoid(float* out, int T, int dim, cudaStream_t s);
+void sinusoid_freqs_host(int dim, float* hf /*[dim / 2]*/);
+void launch_sinusoid(float* out, const float* freq_dev, int T, int dim, cudaStream_t s);
+void launch_sinusoid_t(float* out, const float* freq_dev, const int* t_dev, int B, int dim, cudaStream_t s);
 void launch_silu_f32(const float* in, float* out, int64_t n, cudaStream_t s);
 void launch_t_convert(const int64_t* t, int* out, int B, cudaStream_t s);
 
@@ -87,6 +89,11 @@ void launch_p_losses(const float* x0, const float* noise, const float* x_t, cons
                      const float* sqrt_recipm1_ac, const float* loss_weight, const float* alphas_cumprod,
                      LossArgs a, float* losses, float* parts /*[B][9]*/, int B, cudaStream_t s);
 void launch_loss_dict_mean(const float* parts, float* dict9, int B, cudaStream_t s);
+
+// nearest catalogue model per query object (threed_future_dataset.py:28-77); see k_retrieve
+void launch_retrieve(const int* class_start, int n_classes, const float* cat_feat, const float* cat_size, int feat_dim,
+                     int size_dim, const int64_t* q_label, const float* q_feat, const float* q_size, int Q, int mode,
+                     int64_t* out, cudaStream_t s);
 
 // ---- GEMMs: D[M,N] = act([A0 | A1][M, K0+K1] * W[N, K0+K1]^T + bias) (+ residual) -----------------
 struct GemmArgs {

@@ -937,21 +937,31 @@ __global__ void k_sinusoid(float* __restrict__ out, const float* __restrict__ fr
   out[(int64_t)t * dim + k] = sinf(a);
   out[(int64_t)t * dim + half + k] = cosf(a);
 }
-static float* g_freq = nullptr;
-static int g_freq_dim = 0;
-void launch_sinusoid(float* out, int T, int dim, cudaStream_t s) {
+// frequencies f_k = exp(-k ln(1e4) / (half - 1)), computed on the host in fp32 like the reference's torch.exp on
+// the CPU tensor (denoise_net.py:134-136); the caller owns the device copy (one per handle / device)
+void sinusoid_freqs_host(int dim, float* hf) {
+  const int half = dim / 2;
+  const float neg_emb = -float(9.210340371976184 / double(half - 1));   // -(ln 1e4)/(half-1) as fp32
+  for (int k = 0; k < half; ++k) hf[k] = expf(float(k) * neg_emb);
+}
+void launch_sinusoid(float* out, const float* freq_dev, int T, int dim, cudaStream_t s) {
+  const int half = dim / 2;
+  k_sinusoid<<<cdiv((int64_t)T * half, 256), 256, 0, s>>>(out, freq_dev, T, dim);
+}
+// per-sample variant (training: one timestep per scene): out[b][:] = sinusoid(t[b])
+__global__ void k_sinusoid_t(float* __restrict__ out, const float* __restrict__ freq, const int* __restrict__ t, int B,
+                             int dim) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
   int half = dim / 2;
-  if (g_freq_dim != dim) {
-    if (g_freq) cudaFree(g_freq);
-    cudaMalloc(&g_freq, half * sizeof(float));
-    float* hf = new float[half];
-    const float neg_emb = -float(9.210340371976184 / double(half - 1));   // -(ln 1e4)/(half-1) as fp32
-    for (int k = 0; k < half; ++k) hf[k] = expf(float(k) * neg_emb);
-    cudaMemcpy(g_freq, hf, half * sizeof(float), cudaMemcpyHostToDevice);
-    delete[] hf;
-    g_freq_dim = dim;
-  }
-  k_sinusoid<<<cdiv((int64_t)T * half, 256), 256, 0, s>>>(out, g_freq, T, dim);
+  if (i >= B * half) return;
+  int b = i / half, k = i % half;
+  float a = float(t[b]) * freq[k];
+  out[(int64_t)b * dim + k] = sinf(a);
+  out[(int64_t)b * dim + half + k] = cosf(a);
+}
+void launch_sinusoid_t(float* out, const float* freq_dev, const int* t_dev, int B, int dim, cudaStream_t s) {
+  const int half = dim / 2;
+  k_sinusoid_t<<<cdiv((int64_t)B * half, 256), 256, 0, s>>>(out, freq_dev, t_dev, B, dim);
 }
 
 __global__ void k_silu_f32(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
@@ -1347,5 +1357,88 @@ void init_pointwise_attrs() {
                                    const float*, LossArgs, float*, float*, int, cudaStream_t);
 INST(float)
 INST(bf16)
+
+
+// ------------------------------------------------------------------------------------------------
+// object retrieval: nearest catalogue model per generated object
+// ------------------------------------------------------------------------------------------------
+// Reference: ThreedFutureDataset.get_closest_furniture_to_objfeats_and_size / _to_objfeats / _to_box
+// (scene_synthesis/datasets/threed_future_dataset.py:28-77): among the catalogue entries of the query's class,
+// the entry minimising (size mse, feature mse) lexicographically (np.lexsort((mses_feat, mses_size)): size is the
+// primary key), ties -> first entry in catalogue order.  The catalogue is stored grouped by class (stable), so a
+// class is a contiguous range.  One warp per query; squared distances are accumulated in EXACTLY numpy's order for
+// float32 `np.sum(d ** 2, axis=-1)` (8 running partials over strided elements, then the fixed 3-level tree; plain
+// left-to-right below 8 elements), products and sums rounded separately -- so the keys, not only the winners, are
+// bit-identical to the host computation and ties resolve identically.
+namespace {
+__device__ __forceinline__ float np_sum_sq_diff(const float* __restrict__ a, const float* __restrict__ b, int n) {
+  if (n < 8) {
+    float s = 0.f;      // numpy: res = 0.; res += a[i]
+    for (int i = 0; i < n; ++i) { const float d = __fsub_rn(a[i], b[i]); s = __fadd_rn(s, __fmul_rn(d, d)); }
+    return s;
+  }
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float d = __fsub_rn(a[j], b[j]); r[j] = __fmul_rn(d, d); }
+  int i = 8;
+  for (; i + 8 <= n; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = __fsub_rn(a[i + j], b[i + j]); r[j] = __fadd_rn(r[j], __fmul_rn(d, d)); }
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) { const float d = __fsub_rn(a[i], b[i]); res = __fadd_rn(res, __fmul_rn(d, d)); }
+  return res;
+}
+struct RKey { float k0, k1; int idx; };
+__device__ __forceinline__ bool rkey_less(const RKey& a, const RKey& b) {
+  if (a.k0 != b.k0) return a.k0 < b.k0;
+  if (a.k1 != b.k1) return a.k1 < b.k1;
+  return a.idx < b.idx;
+}
+}  // namespace
+
+// mode 0: (size, feature) lexicographic; 1: feature only; 2: size only
+__global__ void k_retrieve(const int* __restrict__ class_start, int n_classes, const float* __restrict__ cat_feat,
+                           const float* __restrict__ cat_size, int feat_dim, int size_dim,
+                           const int64_t* __restrict__ q_label, const float* __restrict__ q_feat,
+                           const float* __restrict__ q_size, int Q, int mode, int64_t* __restrict__ out) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  const int64_t lab = q_label[q];
+  RKey best;
+  best.k0 = INFINITY; best.k1 = INFINITY; best.idx = 0x7fffffff;
+  if (lab >= 0 && lab < n_classes) {
+    const int beg = class_start[lab], end = class_start[lab + 1];
+    const float* qf = q_feat ? q_feat + (int64_t)q * feat_dim : nullptr;
+    const float* qs = q_size ? q_size + (int64_t)q * size_dim : nullptr;
+    for (int e = beg + lane; e < end; e += 32) {
+      RKey k;
+      k.idx = e;
+      const float mf = mode != 2 ? np_sum_sq_diff(cat_feat + (int64_t)e * feat_dim, qf, feat_dim) : 0.f;
+      const float ms = mode != 1 ? np_sum_sq_diff(cat_size + (int64_t)e * size_dim, qs, size_dim) : 0.f;
+      k.k0 = mode == 1 ? mf : ms;
+      k.k1 = mode == 0 ? mf : 0.f;
+      if (rkey_less(k, best)) best = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    RKey other;
+    other.k0 = __shfl_xor_sync(0xffffffffu, best.k0, o);
+    other.k1 = __shfl_xor_sync(0xffffffffu, best.k1, o);
+    other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+    if (rkey_less(other, best)) best = other;
+  }
+  if (lane == 0) out[q] = best.idx == 0x7fffffff ? -1 : (int64_t)best.idx;
+}
+void launch_retrieve(const int* class_start, int n_classes, const float* cat_feat, const float* cat_size, int feat_dim,
+                     int size_dim, const int64_t* q_label, const float* q_feat, const float* q_size, int Q, int mode,
+                     int64_t* out, cudaStream_t s) {
+  const int wpb = 8;
+  k_retrieve<<<cdiv(Q, wpb), wpb * 32, 0, s>>>(class_start, n_classes, cat_feat, cat_size, feat_dim, size_dim, q_label,
+                                                q_feat, q_size, Q, mode, out);
+}
 
 }  // namespace ds

@@ -175,10 +175,18 @@ class DenoiserEngine:
         dev = self.device
         f = lambda z: None if z is None else z.detach().to(device=dev, dtype=torch.float32).contiguous()
         x_init, noise, partial, partial_noise = f(x_init), f(noise), f(partial), f(partial_noise)
+        if ddim and ddim_times is None:
+            # the reference's grid expression, evaluated by torch itself (fp32 linspace, then .int()):
+            # diffusion_ddpm.py:407-408 -- identical truncation when S does not divide T
+            S = num_steps if num_steps > 0 else 50
+            ddim_times = list(reversed(torch.linspace(-1, self.num_timesteps - 1, steps=S + 1).int().tolist()))
         traj = None
         if traj_freq > 0:
-            n_snap = self.lib.ds_traj_count(num_steps if num_steps > 0 else self.num_timesteps, traj_freq)
-            traj = torch.empty((n_snap, batch, self.num_objects, self.d), device=dev, dtype=torch.float32)
+            if ddim:      # snapshots follow the timestep VALUES the loop visits (engine.cu: ts[i] % freq == 0 or i == 0)
+                n_snap = sum(1 for i, tt in enumerate(ddim_times[:-1]) if tt % traj_freq == 0 or i == 0)
+            else:
+                n_snap = self.lib.ds_traj_count(num_steps if num_steps > 0 else self.num_timesteps, traj_freq)
+            traj = torch.zeros((n_snap, batch, self.num_objects, self.d), device=dev, dtype=torch.float32)
         a = self._sample_args(batch, clip_denoised, num_steps, ddim, ddim_eta, seed, scene_offset, x_init, noise,
                               partial, partial_noise, traj_freq, traj, use_graph, ddim_times, chunk_scenes)
         torch.cuda.current_stream(dev).synchronize()

@@ -11,7 +11,9 @@ Sampling, validation loss and every diffusion step run in the CUDA library.  The
 torch autograd over `functional.DenoiserFn` on the same parameters (native backward is future
 work).  Differences from the reference that are deliberate: the per-call `print`s are gone, `sample()` honours
 `ddim=True` (the reference ignores it and its DDIM loop is dead code), and emptiness is decided per scene when
-batch_size > 1 via `delete_empty_batched` (the reference looks at batch row 0 only).
+batch_size > 1 via `delete_empty_batched` (the reference looks at batch row 0 only).  Like the reference
+(`sample()` dispatches on input_boxes / partial_boxes first, :293-299), `complete_scene` / `arrange_scene` accept
+`ret_traj` / `ddim` and ignore them.
 """
 from __future__ import annotations
 
@@ -62,7 +64,11 @@ class DiffusionSceneLayout_DDPM(nn.Module):
             else:
                 # the frozen BERT encoder runs once per scene outside the denoising loop; it is loaded lazily so
                 # that synthetic `context_cross` tensors can be used without the HF checkpoint (no network here)
-                self.tokenizer, self.bertmodel = None, None
+                # The encoder is frozen and is NOT a registered submodule (object.__setattr__): the state dict of
+                # this class never carries `bertmodel.*`, whether or not BERT has been loaded; reference
+                # checkpoints, which do carry those keys, load through the filter in load_state_dict below.
+                self.tokenizer = None
+                object.__setattr__(self, "bertmodel", None)
                 self.fc_text_f = nn.Linear(768, text_embed_dim)
         if config["net_type"] != "unet1d":
             raise NotImplementedError()
@@ -150,6 +156,17 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         self._engine_version = -1
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.mark_weights_dirty())
 
+    # ---- checkpoints ----------------------------------------------------------------------------
+    FROZEN_PREFIXES = ("bertmodel.", "clip_model.", "feature_extractor.", "fc_room_f.")
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Reference checkpoints of the text configs carry the frozen encoder (`bertmodel.*`: the reference
+        registers it as a submodule, diffusion_scene_layout_ddpm.py:47-48); those keys are dropped here -- the
+        encoder is loaded from its own pretrained files -- so that `strict=True` keeps checking everything that
+        is trained on this path."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith(self.FROZEN_PREFIXES)}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
     # ---- engine management ----------------------------------------------------------------------
     def mark_weights_dirty(self):
         self._weights_version += 1
@@ -221,9 +238,10 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         if self.bertmodel is None:
             from transformers import BertModel, BertTokenizer
             self.tokenizer = BertTokenizer.from_pretrained("bert-base-cased")
-            self.bertmodel = BertModel.from_pretrained("bert-base-cased").to(device).eval()
-            for p in self.bertmodel.parameters():
+            bert = BertModel.from_pretrained("bert-base-cased").to(device).eval()
+            for p in bert.parameters():
                 p.requires_grad = False
+            object.__setattr__(self, "bertmodel", bert)          # frozen, kept out of _modules / state_dict
         tok = self.tokenizer(text, return_tensors="pt", padding=True).to(device)
         with torch.no_grad():
             hid = self.bertmodel(**tok).last_hidden_state
@@ -245,7 +263,9 @@ class DiffusionSceneLayout_DDPM(nn.Module):
             return full[..., :self.bbox_dim].contiguous()
         raise NotImplementedError
 
-    def get_loss(self, sample_params):
+    def get_loss(self, sample_params, t=None, noise=None):
+        """Reference :131-226.  `t` / `noise` (optional) replace the draws of diffusion_ddpm.py:764,767 -- the
+        parity tests inject the numbers the reference drew."""
         target = self._pack_target(sample_params).float()
         B, N, _ = target.shape
         device = target.device
@@ -257,8 +277,8 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         if self.text_condition and "context_cross" in sample_params:
             text = sample_params["context_cross"]
         cross = self._text_condition(text, device) if self.text_condition else None
-        t = torch.randint(0, self.time_num, (B,), device=device)
-        noise = torch.randn_like(target)
+        t = torch.randint(0, self.time_num, (B,), device=device) if t is None else t.to(device)
+        noise = torch.randn_like(target) if noise is None else noise.to(device)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             losses, ld = self._p_losses_autograd(target, t, noise, cond, shared, cross)
         else:
@@ -271,7 +291,10 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         eng.set_context(cond.detach(), shared=shared)
         if self.text_condition:
             eng.set_context_cross(cross.detach())
-        return eng.p_losses(x0, t, noise, self.loss_separate, self.loss_iou, self.bounds)
+        losses, ld = eng.p_losses(x0, t, noise, self.loss_separate, self.loss_iou, self.bounds)
+        if self.room_arrange_condition:      # the reference logs only these two for arrangement (diffusion_ddpm.py:560-572)
+            ld = {k: ld[k] for k in ("loss.trans", "loss.angle")}
+        return losses, ld
 
     def _p_losses_autograd(self, x0, t, noise, cond, shared, cross):
         """p_losses (diffusion_ddpm.py:520-652) with torch autograd for the backward pass."""
@@ -339,7 +362,7 @@ class DiffusionSceneLayout_DDPM(nn.Module):
     @torch.no_grad()
     def sample(self, room_mask, num_points, point_dim, batch_size=1, text=None, partial_boxes=None, input_boxes=None,
                ret_traj=False, ddim=False, clip_denoised=False, freq=40, batch_seeds=None, ddim_steps=50,
-               ddim_eta=0.0, noise=None, x_init=None, seed=None, host_output=False):
+               ddim_eta=0.0, noise=None, x_init=None, seed=None, host_output=False, partial_noise=None):
         device = room_mask.device if torch.is_tensor(room_mask) else self._device()
         if num_points != self.sample_num_points:
             raise ValueError("num_points must equal sample_num_points (%d)" % self.sample_num_points)
@@ -359,7 +382,7 @@ class DiffusionSceneLayout_DDPM(nn.Module):
             ib = input_boxes.to(x.device)
             return torch.cat([x[..., :td], ib[..., td:td + sd], x[..., td:], ib[..., self.bbox_dim:]], dim=-1).contiguous()
         if partial_boxes is not None:
-            return eng.sample(batch_size, partial=partial_boxes, **kw)
+            return eng.sample(batch_size, partial=partial_boxes, partial_noise=partial_noise, **kw)
         if ret_traj:
             x, traj = eng.sample(batch_size, traj_freq=freq, **kw)
             return [None] + list(traj.unbind(0))              # slot 0 stands for x_T (the reference drops it too)
@@ -406,26 +429,37 @@ class DiffusionSceneLayout_DDPM(nn.Module):
 
     @torch.no_grad()
     def delete_empty_from_network_samples(self, samples, device="cpu", keep_empty=False):
-        """Reference semantics: object i is dropped for the WHOLE batch when scene 0 marks it empty
-        (last class channel > 0, diffusion_scene_layout_ddpm.py:379); class scores are returned raw."""
+        """Reference semantics (diffusion_scene_layout_ddpm.py:351-406): object i is dropped for the WHOLE batch
+        when scene 0 marks it empty -- the reference builds `objectness = last class channel >= 0` (:360) and
+        tests that bool with `> 0` (:379), i.e. a score of exactly 0.0 counts as empty; class scores are returned
+        raw (the `one_hot(argmax)` at :358 is computed and discarded)."""
         parts = self._split(samples)
         keep = torch.ones(samples.shape[1], dtype=torch.bool) if keep_empty else \
-            ~(parts["objectness"][0, :, -1] > 0).cpu()
+            ~(parts["objectness"][0, :, -1] >= 0).cpu()
         idx = keep.nonzero().flatten().to(samples.device)
         keys = ["class_labels", "translations", "sizes", "angles"] + (["objfeats"] if self.objfeat_dim > 0 else [])
         return {k: parts[k].index_select(1, idx).to("cpu") for k in keys}
 
     @torch.no_grad()
     def delete_empty_batched(self, samples, keep_empty=False):
-        """Per-scene variant for batch_size > 1: list (one dict per scene) of the non-empty objects, plus the
-        integer class argmax (the north star's bit-exact gate)."""
-        parts = self._split(samples)
-        empty = parts["objectness"][:, :, -1] > 0
+        """Per-scene variant for batch_size > 1 (the reference decides from batch row 0 only): list
+        (one dict per scene) of the non-empty objects, plus the integer class argmax (the north star's bit-exact
+        gate).  The keep mask and the argmax are computed on the device for the whole batch; ONE device->host copy
+        moves the packed result, the per-scene views are cut on the host."""
+        B, N, _ = samples.shape
+        bb, cd = self.bbox_dim, self.class_dim
+        empty = samples[:, :, bb + cd - 1] >= 0
+        keep = torch.ones_like(empty) if keep_empty else ~empty
+        cls_idx = samples[:, :, bb:bb + cd - 1].argmax(dim=-1)
+        packed = torch.cat([samples.float(), keep[..., None].float(), cls_idx[..., None].float()], dim=-1).cpu()
+        keep_h = packed[:, :, -2] > 0.5
+        idx_h = packed[:, :, -1].long()
+        parts = self._split(packed[:, :, :-2])
         out = []
-        for b in range(samples.shape[0]):
-            sel = torch.ones_like(empty[b]) if keep_empty else ~empty[b]
-            d = {k: v[b][sel].to("cpu") for k, v in parts.items() if k != "objectness"}
-            d["class_index"] = d["class_labels"].argmax(dim=-1)
+        for b in range(B):
+            sel = keep_h[b]
+            d = {k: v[b][sel] for k, v in parts.items() if k != "objectness"}
+            d["class_index"] = idx_h[b][sel]
             out.append(d)
         return out
 

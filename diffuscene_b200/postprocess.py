@@ -63,3 +63,55 @@ def post_process_batch(params: Mapping[str, torch.Tensor], bounds: Mapping[str, 
         else:
             out[k] = descale(v, *_lo_hi(bounds, k, v))
     return out
+
+
+class ObjectCatalog:
+    """Device-resident furniture catalogue for batched nearest-model retrieval (the last step of the reference's
+    generation scripts: `ThreedFutureDataset.get_closest_furniture_to_objfeats_and_size` & co,
+    scene_synthesis/datasets/threed_future_dataset.py:28-77, called once per generated object on the CPU).
+
+    labels [M] int class index per catalogue model, feats [M, F] latent shape codes, sizes [M, 3].  The entries are
+    grouped by class once (stable, so catalogue order inside a class -- the reference's tie-break -- is kept);
+    `retrieve` answers a whole [B, N] batch of generated objects with ONE kernel launch (one warp per object) and
+    returns indices into the ORIGINAL catalogue order (-1: class has no model).  Indices are bit-exact with the
+    reference's per-object numpy code (the kernel accumulates in numpy's float32 summation order)."""
+
+    MODES = {"objfeats_and_size": 0, "objfeats": 1, "box": 2}
+
+    def __init__(self, labels, feats, sizes, n_classes=None, device="cuda"):
+        import ctypes as C
+        from . import capi
+        self._C, self._capi = C, capi
+        self.lib = capi.load()
+        labels = torch.as_tensor(labels, dtype=torch.int64).cpu()
+        self.n_classes = int(n_classes if n_classes is not None else (int(labels.max()) + 1 if labels.numel() else 1))
+        order = torch.argsort(labels, stable=True)
+        counts = torch.bincount(labels, minlength=self.n_classes)
+        start = torch.zeros(self.n_classes + 1, dtype=torch.int32)
+        start[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        dev = torch.device(device)
+        self.device = dev
+        self.order = order.to(dev)
+        self.class_start = start.to(dev)
+        self.feats = None if feats is None else torch.as_tensor(feats, dtype=torch.float32)[order].contiguous().to(dev)
+        self.sizes = None if sizes is None else torch.as_tensor(sizes, dtype=torch.float32)[order].contiguous().to(dev)
+
+    def retrieve(self, class_index, objfeats=None, sizes=None, mode="objfeats_and_size"):
+        """class_index [...] int64, objfeats [..., F], sizes [..., 3] (world-space, i.e. after post_process_batch) ->
+        catalogue indices [...] int64 on the device."""
+        m = self.MODES[mode]
+        C = self._C
+        shape = tuple(class_index.shape)
+        ql = class_index.to(self.device, torch.int64).reshape(-1).contiguous()
+        Q = ql.numel()
+        qf = None if objfeats is None else objfeats.to(self.device, torch.float32).reshape(Q, -1).contiguous()
+        qs = None if sizes is None else sizes.to(self.device, torch.float32).reshape(Q, -1).contiguous()
+        out = torch.empty(Q, dtype=torch.int64, device=self.device)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        self._capi.check(self.lib.ds_retrieve_objects(
+            p(self.class_start), self.n_classes, p(self.feats), p(self.sizes),
+            0 if self.feats is None else self.feats.shape[1], 0 if self.sizes is None else self.sizes.shape[1],
+            p(ql), p(qf), p(qs), Q, m, p(out), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        hit = out >= 0
+        res = torch.where(hit, self.order[out.clamp(min=0)], out)
+        return res.reshape(shape)

@@ -171,6 +171,20 @@ DS_API int ds_p_losses(ds_handle* h, const float* x0_dev, const int64_t* t_dev, 
                 int32_t loss_separate, int32_t loss_iou, const float* bounds_host,
                 float* losses_dev, float* loss_dict_dev, int32_t batch, void* stream);
 
+/* ---- post-processing: object retrieval -----------------------------------------------------
+ * Replaces ThreedFutureDataset.get_closest_furniture_to_objfeats_and_size (mode 0), _to_objfeats (mode 1) and
+ * _to_box (mode 2) (scene_synthesis/datasets/threed_future_dataset.py:28-77) for a whole batch of generated objects:
+ * out[q] = index of the catalogue entry of class q_label[q] minimising (size mse, feature mse) lexicographically
+ * (mode 0; np.lexsort((mses_feat, mses_size))), the feature mse (1) or the size mse (2); ties -> lowest index;
+ * -1 when the class has no entry.  The catalogue is grouped by class (stable order inside a class):
+ * class_start[c] .. class_start[c + 1] is the entry range of class c (n_classes + 1 ints).  cat_feat
+ * [n_entries, feat_dim], cat_size [n_entries, size_dim], q_feat [Q, feat_dim], q_size [Q, size_dim] fp32; all
+ * device pointers.  Distances are accumulated in numpy's float32 order, so indices are bit-exact.  Stateless. */
+DS_API int ds_retrieve_objects(const int32_t* class_start_dev, int32_t n_classes, const float* cat_feat_dev,
+                               const float* cat_size_dev, int32_t feat_dim, int32_t size_dim,
+                               const int64_t* q_label_dev, const float* q_feat_dev, const float* q_size_dev,
+                               int32_t num_queries, int32_t mode, int64_t* out_index_dev, void* stream);
+
 /* ---- introspection / debugging ------------------------------------------------------------ */
 /* Human-readable op list of the step program (works without a device when h == NULL: builds the plan
  * for `cfg` on the host only).  Returns bytes written (excluding NUL) or a negative status. */

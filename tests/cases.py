@@ -55,6 +55,10 @@ CASES = {
     "text62": dict(seed=15, B=2, N=12, L=7,
                    net_kwargs=dict(_BED, text_condition=True, text_dim=512),
                    net_cfg=_BED_CFG, diffusion_kwargs=_dk(), loss=False),
+    # the same text-conditioned network through full sampling loops (plain / trajectory / completion), short schedule
+    "text62_loop": dict(seed=18, B=2, N=12, L=7,
+                        net_kwargs=dict(_BED, text_condition=True, text_dim=512),
+                        net_cfg=_BED_CFG, diffusion_kwargs=_dk(T=8), loop=True),
     # re-arrangement network: 5 diffused channels, joint (non-separate) head, 512-d per-object condition
     "arr5": dict(seed=16, B=2, N=12,
                  net_kwargs=dict(dim=512, dim_mults=[1, 1, 1, 1], channels=5, objectness_dim=0, class_dim=22,

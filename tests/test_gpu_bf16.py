@@ -13,6 +13,11 @@ from tests.gpu_common import cuda, get_engine, gold
 
 pytestmark = pytest.mark.gpu
 
+# bf16 throughput-mode gates against the fp32 goldens of the unmodified reference: <= 3x what was measured on B200
+# (bedroom: max 1.7e-3, mean 3.5e-4, class argmax 100 %; the stated north-star figure "within 1e-3" is met by the
+# fp32 parity mode only).  bench.py prints the measured value of the benched precision (`parity_max_abs`).
+BF16_MAX, BF16_MEAN, BF16_ARGMAX = 5e-3, 1e-3, 0.99
+
 
 def _gemm(backend, a, w, bias, act=0):
     lib = capi.load()
@@ -52,11 +57,12 @@ def test_forward_error_bound(name, backend, golden_dir):
     out = eng.forward(cuda(inp["x"]), cuda(inp["t"])).cpu()
     err = (out - g).abs()
     # bf16 storage + bf16 weights, fp32 accumulate: the reference probe saw max 1.8e-3
-    assert err.max() < 2e-2 and err.mean() < 4e-3, (err.max().item(), err.mean().item())
+    print("bf16 forward error %s/%s: max %.3g mean %.3g" % (name, backend, err.max().item(), err.mean().item()))
+    assert err.max() < BF16_MAX and err.mean() < BF16_MEAN, (err.max().item(), err.mean().item())
     if spec.seperate_all:
         b0 = spec.bbox_dim
         agree = (out[..., b0:b0 + spec.class_dim - 1].argmax(-1) == g[..., b0:b0 + spec.class_dim - 1].argmax(-1))
-        assert agree.float().mean() >= 0.9
+        assert agree.float().mean() >= BF16_ARGMAX
 
 
 @pytest.mark.parametrize("name", ["bed62", "liv65", "arr5"])
@@ -87,8 +93,8 @@ def test_channels_on_lanes_groupnorm_gemm(name, fuse, golden_dir):
     a = e2.forward(cuda(inp["x"]), cuda(inp["t"])).cpu()
     b = e1.forward(cuda(inp["x"]), cuda(inp["t"])).cpu()
     err = (a - g).abs()
-    assert err.max() < 2e-2 and err.mean() < 4e-3, (err.max().item(), err.mean().item())
-    assert (a - b).abs().max().item() < 2e-2
+    assert err.max() < BF16_MAX and err.mean() < BF16_MEAN, (err.max().item(), err.mean().item())
+    assert (a - b).abs().max().item() < 2 * BF16_MAX
     assert (a - g).abs().mean() <= (b - g).abs().mean() * 1.5 + 1e-4
 
 
@@ -188,3 +194,30 @@ def test_full_sample_smoke_bf16():
     assert torch.isfinite(out).all()
     out_h = eng.sample(256, seed=11, host_output=True)
     assert torch.equal(out_h, out.cpu())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_large_batch_against_oracle(prec):
+    """Oracle comparison at a batch with a ragged last tile (B = 1003 scenes: 62 full 16-scene tiles + 11): every
+    scene is checked against the CPU oracle, per-scene timesteps, in both precisions."""
+    from oracle.unet1d_ref import unet1d_forward
+    from diffuscene_b200.weights import seeded_state_dict, unet1d_param_specs
+    eng, case, spec, inp = get_engine("bed62", prec)
+    B, N = 1003, case["N"]
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(B, N, spec.point_dim, generator=gen)
+    t = torch.randint(0, case["diffusion_kwargs"]["time_num"], (B,), generator=gen)
+    sd = seeded_state_dict(unet1d_param_specs(spec), seed=case["seed"])
+    ctx = inp["context"][0][None].expand(B, N, spec.cond_dim).contiguous()
+    with torch.no_grad():
+        ref = unet1d_forward(sd, spec, x, t, ctx, None)
+    out = eng.forward(x.cuda(), t.cuda()).cpu()
+    err = (out - ref).abs()
+    b0 = spec.bbox_dim
+    agree = (out[..., b0:b0 + spec.class_dim - 1].argmax(-1) == ref[..., b0:b0 + spec.class_dim - 1].argmax(-1)).float().mean()
+    print("B=1003 %s: max %.3g mean %.3g argmax agreement %.5f" % (prec, err.max().item(), err.mean().item(), agree.item()))
+    if prec == "fp32":
+        assert torch.allclose(out, ref, rtol=1e-3, atol=1e-4)
+        assert agree == 1.0
+    else:
+        assert err.max() < 2 * BF16_MAX and err.mean() < BF16_MEAN and agree >= BF16_ARGMAX      # max over 750k outputs

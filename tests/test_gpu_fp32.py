@@ -40,9 +40,10 @@ def _stack_noise(stream, n, shape):
     return torch.stack([stream(shape) for _ in range(n)])
 
 
-def test_sampling_loops_parity(golden_dir):
-    eng, case, spec, inp = get_engine("bed62_loop", "fp32")
-    g = gold(golden_dir, "bed62_loop")
+@pytest.mark.parametrize("name", ["bed62_loop", "text62_loop"])
+def test_sampling_loops_parity(name, golden_dir):
+    eng, case, spec, inp = get_engine(name, "fp32")
+    g = gold(golden_dir, name)
     T = case["diffusion_kwargs"]["time_num"]
     shape = tuple(inp["x"].shape)
     loop_tol = dict(rtol=2e-3, atol=2e-4)

@@ -66,10 +66,11 @@ def test_losses(name, golden_dir):
             np.testing.assert_allclose(float(v), float(gold["ld." + k]), **TOL)
 
 
-def test_loops(golden_dir):
+@pytest.mark.parametrize("name", ["bed62_loop", "text62_loop"])
+def test_loops(name, golden_dir):
     torch.set_grad_enabled(False)
-    gold = np.load(os.path.join(golden_dir, "bed62_loop.npz"))
-    case, spec, inp, sched, denoise = _setup("bed62_loop")
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    case, spec, inp, sched, denoise = _setup(name)
     shape = tuple(inp["x"].shape)
     loop_tol = dict(rtol=1e-3, atol=1e-4)
     x = D.p_sample_loop(sched, denoise, shape, noise_stream(case["seed"] + 100))
