@@ -1,0 +1,43 @@
+#!/bin/bash
+# One parametrised GPU-box runner (use through gpurun):  scripts/gpu_run.sh <tag> <task> [args...]
+#   tests [pytest args]     GPU test suite (default: everything marked gpu)
+#   bench [bench args]      one bench.py run, JSON line -> gpurun_out/<tag>_bench.json
+#   ops   [bench args]      per-op device-time table of one step program -> gpurun_out/<tag>_per_op_us.txt
+#   launches [bench args]   ncu launch list (time + DRAM bytes) of a short bench -> gpurun_out/<tag>_launches.csv
+#   full <kernel-regex> [skip] [count]   one `ncu --set full` capture -> gpurun_out/<tag>_<...>.ncu-rep
+# Several tasks can be chained with "--":  gpu_run.sh r2 tests -- bench --steps 2
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TAG=$1; shift
+run_task() {
+  local task=$1; shift
+  case "$task" in
+    tests)
+      if [ $# -eq 0 ]; then set -- tests/; fi
+      timeout 1500 python -m pytest "$@" -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/${TAG}_tests.log ;;
+    bench)
+      timeout 900 python bench.py "$@" > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+      tail -c 1500 gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json ;;
+    ops)
+      timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-ops "$@" 2> gpurun_out/${TAG}_per_op_us.txt | cut -c1-300
+      tail -n +1 gpurun_out/${TAG}_per_op_us.txt | head -150 ;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+        -c 2000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --timesteps 3 \
+        --no-cpu-baseline --no-e2e "$@" > gpurun_out/${TAG}_launches.log 2>&1
+      tail -3 gpurun_out/${TAG}_launches.log | cut -c1-300; wc -l gpurun_out/${TAG}_launches.csv ;;
+    full)
+      local k=$1; local skip=${2:-60}; local cnt=${3:-3}
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c $cnt \
+        -o gpurun_out/${TAG}_$(echo $k | tr -c 'a-zA-Z0-9\n' _)_full -f python bench.py --steps 1 --warmup 1 --timesteps 2 \
+        --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_full.log 2>&1
+      tail -2 gpurun_out/${TAG}_full.log | cut -c1-300; ls -la gpurun_out/${TAG}_*.ncu-rep ;;
+    *) echo "unknown task $task"; return 2 ;;
+  esac
+}
+args=()
+for a in "$@"; do
+  if [ "$a" == "--" ]; then run_task "${args[@]}"; args=(); else args+=("$a"); fi
+done
+[ ${#args[@]} -gt 0 ] && run_task "${args[@]}"
+echo "gpu_run done"
