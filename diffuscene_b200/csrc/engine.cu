@@ -62,7 +62,7 @@ struct ds_handle {
   bool ctx_shared = false, ctx_set = false;
   std::vector<float*> kv_w;
   float* xctx = nullptr;
-  int xctx_batch = 0;
+  int xctx_batch = 0, xctx_cap = 0;
   // activations
   int cap_scenes = 0, rows_cap = 0;
   std::vector<void*> bufs;
@@ -81,7 +81,28 @@ struct ds_handle {
   StepState* state_dev = nullptr;
   int64_t launches = 0;
   int t_uniform = 0;          // 1 while every entry of t_dev is the same (inside the sampling loop)
+  // instantiated step graph, reused across ds_sample_loop calls whose captured parameters agree (batch, flags,
+  // injected-buffer pointers); seed / scene offset / coefficients live in device memory and are not captured
+  struct GraphKey {
+    int batch = -1, clip = 0, num_partial = 0, plan_gen = 0;
+    const void *noise = nullptr, *partial = nullptr, *partial_noise = nullptr;
+    cudaStream_t stream = nullptr;
+    bool operator==(const GraphKey& o) const {
+      return batch == o.batch && clip == o.clip && num_partial == o.num_partial && plan_gen == o.plan_gen &&
+             noise == o.noise && partial == o.partial && partial_noise == o.partial_noise && stream == o.stream;
+    }
+  } gkey;
+  cudaGraphExec_t gexec = nullptr;
+  int64_t g_launches = 0;     // kernel launches inside one replay
+  int plan_gen = 0;           // bumped whenever buffers / tensor maps / tables are rebuilt
+  int64_t graph_builds = 0;
 };
+static void drop_graph(ds_handle* h) {
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  h->gexec = nullptr;
+  h->gkey = ds_handle::GraphKey();
+  h->plan_gen++;
+}
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -187,6 +208,7 @@ static int run_forward(ds_handle* h, const float* x, int n_scenes, cudaStream_t 
 // capacity / buffers
 // ------------------------------------------------------------------------------------------------
 static void free_buffers(ds_handle* h) {
+  drop_graph(h);
   for (void* p : h->bufs) cudaFree(p);
   h->bufs.clear();
   for (auto* p : h->tc) if (p) tc_plan_destroy(p);
@@ -526,6 +548,7 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
 extern "C" int ds_destroy(ds_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
+  drop_graph(h);
   free_buffers(h);
   cudaFree(h->warena); cudaFree(h->varena);
   cudaFree(h->time_w1); cudaFree(h->time_b1); cudaFree(h->time_w3); cudaFree(h->time_b3);
@@ -602,6 +625,7 @@ extern "C" int ds_set_context(ds_handle* h, const float* context_dev, int32_t ba
   const int rows = shared ? h->cfg.num_objects : batch * h->cfg.num_objects;
   if (rows <= 0) return fail(DS_ERR_INVALID, "bad context batch");
   if (rows > h->ctx_rows) {
+    drop_graph(h);
     cudaFree(h->ctx_table);
     h->ctx_table = nullptr;
     CK(cudaMalloc(&h->ctx_table, (size_t)rows * ncb * 2 * C * 4));
@@ -617,6 +641,7 @@ extern "C" int ds_set_context(ds_handle* h, const float* context_dev, int32_t ba
   launch_gemm_f32(g, s);
   CK(cudaFreeAsync(act, s));
   h->launches += 2;
+  if ((shared != 0) != h->ctx_shared || !h->ctx_set) drop_graph(h);     // FiLM mode is baked into the captured launches
   h->ctx_shared = shared != 0;
   h->ctx_batch = shared ? 0 : batch;
   h->ctx_set = true;
@@ -635,9 +660,13 @@ extern "C" int ds_set_context_cross(ds_handle* h, const float* cross_dev, int32_
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
   const int nl = int(h->plan.xattn_layers.size()), TD = h->cfg.text_dim;
-  cudaFree(h->xctx);
-  h->xctx = nullptr;
-  CK(cudaMalloc(&h->xctx, (size_t)nl * batch * 4096 * 4));
+  if (batch != h->xctx_cap) {
+    drop_graph(h);
+    cudaFree(h->xctx);
+    h->xctx = nullptr;
+    CK(cudaMalloc(&h->xctx, (size_t)nl * batch * 4096 * 4));
+    h->xctx_cap = batch;
+  }
   float* kv = nullptr;
   CK(cudaMallocAsync(&kv, (size_t)batch * L * 256 * 4, s));
   for (int l = 0; l < nl; ++l) {
@@ -729,17 +758,17 @@ static int step_body(ds_handle* h, const ds_sample_args* a, cudaStream_t s) {
   struct Uni { ds_handle* h; Uni(ds_handle* x) : h(x) { h->t_uniform = 1; } ~Uni() { h->t_uniform = 0; } } uni(h);
   const int B = a->batch, n_obj = h->cfg.num_objects;
   launch_begin_step(h->coef_dev, h->state_dev, h->t_dev, h->x_state, a->partial_dev, a->partial_noise_dev, B, n_obj,
-                    P.d, a->partial_dev ? a->num_partial : 0, a->seed, a->scene_offset, s);
+                    P.d, a->partial_dev ? a->num_partial : 0, s);
   h->launches++;
   int rc = run_forward(h, h->x_state, B, s);
   if (rc) return rc;
   const int clip = a->ddim ? 1 : a->clip_denoised;
   if (h->bf16_mode)
     launch_step_update<bf16>(h->coef_dev, h->state_dev, h->x_state, (const bf16*)h->bufs[P.out_buf], P.dpad,
-                             a->noise_dev, B, n_obj, P.d, clip, a->seed, a->scene_offset, s);
+                             a->noise_dev, B, n_obj, P.d, clip, s);
   else
     launch_step_update<float>(h->coef_dev, h->state_dev, h->x_state, (const float*)h->bufs[P.out_buf], P.dpad,
-                              a->noise_dev, B, n_obj, P.d, clip, a->seed, a->scene_offset, s);
+                              a->noise_dev, B, n_obj, P.d, clip, s);
   h->launches++;
   return 0;
 }
@@ -833,8 +862,10 @@ extern "C" int ds_sample_loop(ds_handle* h, const ds_sample_args* a, float* out_
     h->coef_cap = n_steps;
   }
   CK(cudaMemcpyAsync(h->coef_dev, coef.data(), sizeof(StepCoef) * n_steps, cudaMemcpyHostToDevice, s));
-  CK(cudaMemsetAsync(h->state_dev, 0, sizeof(StepState), s));
-  CK(cudaStreamSynchronize(s));      // coef is a local vector
+  StepState st0;
+  st0.step = 0; st0.done = 0; st0.seed = a->seed; st0.scene_offset = a->scene_offset;
+  CK(cudaMemcpyAsync(h->state_dev, &st0, sizeof(StepState), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));      // coef / st0 are locals
 
   const size_t xs = (size_t)B * n_obj * P.d * sizeof(float);
   if (a->x_init_dev) CK(cudaMemcpyAsync(h->x_state, a->x_init_dev, xs, cudaMemcpyDeviceToDevice, s));
@@ -843,19 +874,32 @@ extern "C" int ds_sample_loop(ds_handle* h, const ds_sample_args* a, float* out_
     h->launches++;
   }
 
-  cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   int64_t launches_per_step = 0;
   if (a->use_graph) {
-    int64_t l0 = h->launches;
-    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = step_body(h, a, s);
-    cudaError_t ce = cudaStreamEndCapture(s, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return fail(DS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    CK(cudaGraphInstantiate(&gexec, graph, 0));
-    launches_per_step = h->launches - l0;
-    h->launches = l0;
+    ds_handle::GraphKey key;
+    key.batch = B; key.clip = a->ddim ? 1 : a->clip_denoised; key.num_partial = a->partial_dev ? a->num_partial : 0;
+    key.plan_gen = h->plan_gen; key.noise = a->noise_dev; key.partial = a->partial_dev;
+    key.partial_noise = a->partial_noise_dev; key.stream = s;
+    if (!h->gexec || !(h->gkey == key)) {
+      if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      int64_t l0 = h->launches;
+      CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      rc = step_body(h, a, s);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail(DS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { h->gexec = nullptr; return fail(DS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+      h->g_launches = h->launches - l0;
+      h->launches = l0;
+      h->gkey = key;
+      h->graph_builds++;
+    }
+    gexec = h->gexec;
+    launches_per_step = h->g_launches;
   }
   int snap = 0;
   for (int i = 0; i < n_steps; ++i) {
@@ -877,13 +921,7 @@ extern "C" int ds_sample_loop(ds_handle* h, const ds_sample_args* a, float* out_
   }
   CK(cudaMemcpyAsync(out_dev, h->x_state, xs, cudaMemcpyDeviceToDevice, s));
   cudaError_t le = cudaGetLastError();
-  if (gexec) {
-    CK(cudaStreamSynchronize(s));
-    cudaGraphExecDestroy(gexec);
-    cudaGraphDestroy(graph);
-  } else if (!stream) {
-    CK(cudaStreamSynchronize(s));
-  }
+  if (gexec || !stream) CK(cudaStreamSynchronize(s));      // the caller's injected buffers may go away after the call
   if (le != cudaSuccess) return fail(DS_ERR_CUDA, "sampling loop: %s", cudaGetErrorString(le));
   if (tc_error_flag()) return fail(DS_ERR_CUDA, "tcgen05 pipeline timeout (code %d)", tc_error_flag());
   return 0;
@@ -1078,6 +1116,7 @@ extern "C" int ds_read_tap(ds_handle* h, const char* name, float* host_out, int6
 }
 
 extern "C" int64_t ds_launch_count(ds_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t ds_graph_build_count(ds_handle* h) { return h ? h->graph_builds : 0; }
 extern "C" int32_t ds_gnt_weight_row(int32_t stored_row) { return tc_gnt_row(stored_row); }
 
 extern "C" int ds_profile_ops(ds_handle* h, int32_t batch, char* names_buf, int64_t names_len, float* usec,

@@ -57,16 +57,18 @@ struct StepCoef {
 struct StepState {        // device-resident loop state (advanced by the kernels themselves), one per handle
   int step;               // loop iteration index (0 .. n_steps-1)
   unsigned int done;      // blocks of the running step_update kernel that have finished (last one advances `step`)
+  // Philox key / global index of scene 0 of this call: read from HERE by the step kernels (not passed as kernel
+  // parameters), so that a captured step graph is reusable across calls with different seeds / shards
+  unsigned long long seed;
+  unsigned long long scene_offset;
 };
 // start of a step: t_dev[b] = coef[step].t ; optional completion re-noise of the first P objects
 void launch_begin_step(const StepCoef* coef, const StepState* st, int* t_dev, float* x, const float* partial,
-                       const float* partial_noise, int B, int n_obj, int d, int P, uint64_t seed,
-                       uint64_t scene_offset, cudaStream_t s);
+                       const float* partial_noise, int B, int n_obj, int d, int P, cudaStream_t s);
 // end of a step: x <- update(x, model_out, noise) ; advances st->step
 template <typename T>
 void launch_step_update(const StepCoef* coef, StepState* st, float* x, const T* model_out, int ld_out,
-                        const float* noise, int B, int n_obj, int d, int clip, uint64_t seed,
-                        uint64_t scene_offset, cudaStream_t s);
+                        const float* noise, int B, int n_obj, int d, int clip, cudaStream_t s);
 void launch_randn(float* out, int B, int per_scene, uint64_t seed, uint64_t scene_offset, uint32_t stream_id,
                   cudaStream_t s);
 // single explicit reverse step with per-sample t (p_sample)

@@ -993,9 +993,9 @@ __device__ __forceinline__ float4 randn4(uint64_t seed, uint64_t gs, uint32_t qd
 
 __global__ void k_begin_step(const StepCoef* __restrict__ coef, const StepState* __restrict__ st,
                              int* __restrict__ t_dev, float* __restrict__ x, const float* __restrict__ partial,
-                             const float* __restrict__ partial_noise, int B, int n_obj, int d, int P, uint64_t seed,
-                             uint64_t scene_offset) {
+                             const float* __restrict__ partial_noise, int B, int n_obj, int d, int P) {
   const int step = st->step;
+  const uint64_t seed = st->seed, scene_offset = st->scene_offset;
   const StepCoef c = coef[step];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < B) t_dev[i] = c.t;
@@ -1025,15 +1025,13 @@ __global__ void k_begin_step(const StepCoef* __restrict__ coef, const StepState*
   }
 }
 void launch_begin_step(const StepCoef* coef, const StepState* st, int* t_dev, float* x, const float* partial,
-                       const float* partial_noise, int B, int n_obj, int d, int P, uint64_t seed,
-                       uint64_t scene_offset, cudaStream_t s) {
+                       const float* partial_noise, int B, int n_obj, int d, int P, cudaStream_t s) {
   int64_t n = B;
   if (P > 0) {
     int64_t m = (int64_t)B * ((P * d + 3) / 4);
     if (m > n) n = m;
   }
-  k_begin_step<<<cdiv(n, 256), 256, 0, s>>>(coef, st, t_dev, x, partial, partial_noise, B, n_obj, d, P, seed,
-                                            scene_offset);
+  k_begin_step<<<cdiv(n, 256), 256, 0, s>>>(coef, st, t_dev, x, partial, partial_noise, B, n_obj, d, P);
 }
 
 // x0 = a_x*x + a_o*out ; clamp ; x' = c_0*x0 + c_x*x + c_z*z   (rounding order of diffusion_ddpm.py:236-240,
@@ -1041,8 +1039,9 @@ void launch_begin_step(const StepCoef* coef, const StepState* st, int* t_dev, fl
 template <typename T>
 __global__ void k_step_update(const StepCoef* __restrict__ coef, StepState* st, float* __restrict__ x,
                               const T* __restrict__ model_out, int ld_out, const float* __restrict__ noise, int B,
-                              int n_obj, int d, int clip, uint64_t seed, uint64_t scene_offset) {
+                              int n_obj, int d, int clip) {
   const int step = st->step;
+  const uint64_t seed = st->seed, scene_offset = st->scene_offset;
   const StepCoef c = coef[step];
   const int per_scene = n_obj * d, quads = (per_scene + 3) / 4;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1090,11 +1089,9 @@ __global__ void k_step_update(const StepCoef* __restrict__ coef, StepState* st, 
 }
 template <typename T>
 void launch_step_update(const StepCoef* coef, StepState* st, float* x, const T* model_out, int ld_out,
-                        const float* noise, int B, int n_obj, int d, int clip, uint64_t seed, uint64_t scene_offset,
-                        cudaStream_t s) {
+                        const float* noise, int B, int n_obj, int d, int clip, cudaStream_t s) {
   int64_t n = (int64_t)B * ((n_obj * d + 3) / 4);
-  k_step_update<T><<<cdiv(n, 256), 256, 0, s>>>(coef, st, x, model_out, ld_out, noise, B, n_obj, d, clip, seed,
-                                                scene_offset);
+  k_step_update<T><<<cdiv(n, 256), 256, 0, s>>>(coef, st, x, model_out, ld_out, noise, B, n_obj, d, clip);
 }
 
 __global__ void k_randn(float* __restrict__ out, int B, int per_scene, uint64_t seed, uint64_t scene_offset,
@@ -1348,7 +1345,7 @@ void init_pointwise_attrs() {
   template void launch_softattn<T>(const T*, int, T*, int, int, int, cudaStream_t);                               \
   template void launch_xattn_apply<T>(const T*, int, const float*, T*, int, int, int, cudaStream_t);              \
   template void launch_step_update<T>(const StepCoef*, StepState*, float*, const T*, int, const float*, int, int, \
-                                      int, int, uint64_t, uint64_t, cudaStream_t);                                \
+                                      int, int, cudaStream_t);                                                    \
   template void launch_p_sample<T>(const float*, const T*, int, const int*, const float*, float*, const float*,   \
                                    const float*, const float*, const float*, const float*, int, int, int, int,    \
                                    cudaStream_t);                                                                 \

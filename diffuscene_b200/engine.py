@@ -239,6 +239,9 @@ class DenoiserEngine:
     def launch_count(self) -> int:
         return int(self.lib.ds_launch_count(self.h))
 
+    def graph_build_count(self) -> int:
+        return int(self.lib.ds_graph_build_count(self.h))
+
     def profile_ops(self, batch: int):
         names = C.create_string_buffer(1 << 16)
         us = (C.c_float * 1024)()

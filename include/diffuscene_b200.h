@@ -197,6 +197,9 @@ DS_API int ds_enable_taps(ds_handle* h, int32_t on);
 DS_API int ds_read_tap(ds_handle* h, const char* name, float* host_out, int64_t capacity, int32_t* rows, int32_t* width);
 /* Kernel launches issued by this handle since creation (ours only; no library kernels exist). */
 DS_API int64_t ds_launch_count(ds_handle* h);
+/* How many times ds_sample_loop had to capture + instantiate its step graph (it is cached across calls whose
+ * batch / flags / injected-buffer pointers agree; seeds and shard offsets live in device memory). */
+DS_API int64_t ds_graph_build_count(ds_handle* h);
 /* Weight layout of the channels-on-lanes GEMM (fuse_level >= 2): the output channel whose weights are stored in row
  * `stored_row` of a packed [N, K] matrix.  Host-only (no device needed); identity for the row-major kernels. */
 DS_API int32_t ds_gnt_weight_row(int32_t stored_row);

@@ -14,7 +14,8 @@ run_task() {
   case "$task" in
     tests)
       if [ $# -eq 0 ]; then set -- tests/; fi
-      timeout 1500 python -m pytest "$@" -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/${TAG}_tests.log ;;
+      timeout 1500 python -m pytest "$@" -q -m gpu --timeout 300 -p no:cacheprovider -rA > gpurun_out/${TAG}_tests.log 2>&1
+      grep -E "^(PASSED|FAILED|ERROR)|passed|failed|error" gpurun_out/${TAG}_tests.log | grep -v "^PASSED" | tail -40 ;;
     bench)
       timeout 900 python bench.py "$@" > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
       tail -c 1500 gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json ;;

@@ -172,6 +172,7 @@ def main():
                 # the reference's post-processing concatenates onto batch-1 buffers (:364-371): batch_size must be 1
                 kw1 = {k: v[:1] for k, v in kw.items()}
                 boxes = net.generate_layout(room[:1], N, d, batch_size=1, clip_denoised=True, **kw1)
+            out["layout_draws"] = np.stack([a.numpy() for a in r.randn_draws[1:]])     # batch-1 draws of this call
             for k, v in boxes.items():
                 out["layout." + k] = v.numpy()
         # ---- post-processing on a crafted batch (zeros, signs, ties) --------------------------------------

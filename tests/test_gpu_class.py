@@ -78,7 +78,8 @@ def test_sample_matches_reference_class(name, tmp_path, golden_dir):
         cl = slice(8, 8 + 21)
         assert np.array_equal(out.cpu().numpy()[..., cl].argmax(-1), ref[..., cl].argmax(-1))      # integer class argmax
         # generate_layout = sample + delete_empty_from_network_samples (batch 1, like the reference's script)
-        kw1 = dict(kw, x_init=draws[0][:1], noise=draws[1:, :1])
+        d1 = torch.from_numpy(g["layout_draws"])
+        kw1 = dict(kw, x_init=d1[0], noise=d1[1:])
         if case.get("text"):
             kw1["text"] = kw["text"][:1]
         s1 = net.sample(room[:1], N, 62, batch_size=1, **kw1)
