@@ -143,6 +143,7 @@ class CpuArm:
         self.text = bool(kw.get("text_condition"))
         torch.set_grad_enabled(False)
         self.threads = threads or _cpu_threads()
+        self.cores_available = _cpu_threads()
         torch.set_num_threads(self.threads)
         self.kind = "port"
         self.net = None
@@ -169,8 +170,55 @@ class CpuArm:
             self.sched = D.make_schedule(D.make_betas("linear", 1e-4, 0.02, 1000), "v", "fixedsmall")
             self.D = D
 
+    def tune_threads(self):
+        """"All the host threads it can use": torch's CPU kernels at these sizes stop scaling (and oversubscribe) well
+        before a large host's core count, so one diffusion step is timed at {all cores, 64, 32, 16} threads and the
+        fastest setting is kept; `cores` in the JSON is the thread count actually used."""
+        if getattr(self, "_tuned", False) or self.cores_available <= 16:
+            return
+        global CPU_K
+        best, k0 = None, CPU_K
+        for n in sorted({self.cores_available, 64, 32, 16}, reverse=True):
+            if n > self.cores_available:
+                continue
+            torch.set_num_threads(n)
+            self._one(32, 1)
+            dt = self._one(32, 1)
+            if best is None or dt < best[0]:
+                best = (dt, n)
+        self.threads = best[1]
+        torch.set_num_threads(self.threads)
+        self._tuned = True
+
+    def _one(self, B, K):
+        """K denoiser evaluations + posterior updates of B scenes through the same code path as step()."""
+        N, d = self.N, self.d
+        t0 = time.perf_counter()
+        if self.net is not None:
+            import contextlib
+            import io
+            # a K-step schedule would need a rebuilt network; time the denoiser + one reverse step directly instead
+            dp = self.net.diffusion
+            x = torch.randn(B, N, d)
+            cond = self.net.positional_embedding[None].expand(B, -1, -1)
+            with contextlib.redirect_stdout(io.StringIO()):
+                for _ in range(K):
+                    t = torch.zeros(B, dtype=torch.int64)
+                    x = dp.diffusion.p_sample(dp._denoise, x, t, cond, None, torch.randn, clip_denoised=True)
+        else:
+            from oracle.unet1d_ref import unet1d_forward
+            ctx = torch.randn(N, 128)[None].expand(B, N, 128).contiguous()
+            cross = torch.randn(B, TEXT_L, 512) if self.text else None
+            x = torch.randn(B, N, d)
+            den = lambda xx, tt: unet1d_forward(self.sd, self.spec, xx, tt, ctx, cross)
+            for _ in range(K):
+                t = torch.full((B,), 500, dtype=torch.int64)
+                x, _ = self.D.p_sample_step(self.sched, den, x, t, torch.randn_like(x), True)
+        return time.perf_counter() - t0
+
     def step(self):
         """One bench step of the CPU arm = K diffusion steps of B scenes; returns seconds per diffusion step."""
+        self.tune_threads()
         B, K, N, d = CPU_B, CPU_K, self.N, self.d
         if self.net is not None:
             import contextlib
@@ -217,8 +265,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sec_per_dstep * CPU_K,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s, T=%d DDPM sampling" % (label, T), "name": args.config},
-        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": arm.threads, "kind": arm.kind, "sample": arm.describe(T),
-                         "sec_per_scene_step": sec_per_dstep / CPU_B},
+        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": arm.threads, "cores_available": arm.cores_available,
+                         "kind": arm.kind, "sample": arm.describe(T), "sec_per_scene_step": sec_per_dstep / CPU_B},
         "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -423,8 +471,8 @@ def main():
             arm.step()
             sec = arm.step()
             v = CPU_B / (sec * T)
-            res["cpu_baseline"] = {"value": v, "unit": "scenes/s", "cores": arm.threads, "kind": arm.kind,
-                                   "sample": arm.describe(T), "sec_per_scene_step": sec / CPU_B}
+            res["cpu_baseline"] = {"value": v, "unit": "scenes/s", "cores": arm.threads, "cores_available": arm.cores_available,
+                                   "kind": arm.kind, "sample": arm.describe(T), "sec_per_scene_step": sec / CPU_B}
             from oracle.unet1d_ref import unet1d_forward
             sd = seeded_state_dict(unet1d_param_specs(spec), seed=0)
             pb = min(B, 8)

@@ -67,6 +67,7 @@ struct ds_handle {
   int cap_scenes = 0, rows_cap = 0;
   std::vector<void*> bufs;
   std::vector<TcGemmPlan*> tc;
+  std::vector<LnGemmPlan*> lnp;      // fused GEMM + LayerNorm ops
   int* t_dev = nullptr;
   float* x_state = nullptr;      // [cap, N, d] running sample
   float* x_tmp = nullptr;        // [cap, N, d] scratch (q_sample / host staging)
@@ -136,6 +137,13 @@ static int run_op(ds_handle* h, int idx, int n_scenes, cudaStream_t s) {
   switch (o.kind) {
     case OP_PACK:
       return DS_ERR_STATE;   // handled by the caller (needs the x pointer)
+    case OP_GEMM_LN: {
+      if (!h->use_tc || !h->lnp[idx]) return fail(DS_ERR_STATE, "fused LayerNorm op without the tcgen05 backend");
+      int e = launch_gemm_ln(h->lnp[idx], M, s);
+      if (e) return fail(DS_ERR_CUDA, "tcgen05 GEMM+LayerNorm launch '%s' failed: %s", o.name.c_str(),
+                         cudaGetErrorString((cudaError_t)e));
+      break;
+    }
     case OP_GEMM_GN:
       if (!h->use_tc) return fail(DS_ERR_STATE, "fused GroupNorm op without the tcgen05 backend");
       // fallthrough
@@ -213,6 +221,8 @@ static void free_buffers(ds_handle* h) {
   h->bufs.clear();
   for (auto* p : h->tc) if (p) tc_plan_destroy(p);
   h->tc.clear();
+  for (auto* p : h->lnp) if (p) ln_plan_destroy(p);
+  h->lnp.clear();
   cudaFree(h->t_dev); h->t_dev = nullptr;
   cudaFree(h->x_state); h->x_state = nullptr;
   cudaFree(h->x_tmp); h->x_tmp = nullptr;
@@ -257,13 +267,27 @@ static int ensure_capacity(ds_handle* h, int n_scenes) {
   CK(cudaMalloc(&h->t64_tmp, sizeof(int64_t) * n_scenes));
   CK(cudaMalloc(&h->loss_parts, sizeof(float) * 9 * n_scenes));
   h->tc.assign(P.ops.size(), nullptr);
+  h->lnp.assign(P.ops.size(), nullptr);
   if (h->use_tc) {
     for (size_t i = 0; i < P.ops.size(); ++i) {
       const Op& o = P.ops[i];
-      if (o.kind != OP_GEMM && o.kind != OP_GEMM_GN) continue;
+      if (o.kind != OP_GEMM && o.kind != OP_GEMM_GN && o.kind != OP_GEMM_LN) continue;
       auto ptr = [&](int buf, int col) -> bf16* { return buf < 0 ? nullptr : (bf16*)h->bufs[buf] + col; };
       GemmArgs g;
       memset(&g, 0, sizeof g);
+      if (o.kind == OP_GEMM_LN) {
+        g.a0 = ptr(o.in0.buf, o.in0.col); g.lda0 = P.buf_width[o.in0.buf]; g.k0 = o.in0.k;
+        g.w = h->warena + h->w_off[o.w]; g.ldw = P.wmats[o.w].K;
+        g.bias = o.b >= 0 ? h->varena + h->v_off[o.b] : nullptr;
+        g.gamma = h->varena + h->v_off[o.gamma];
+        g.d = ptr(o.out, o.out_col); g.ldd = P.buf_width[o.out];
+        g.res = ptr(o.res, 0); g.ldres = o.res >= 0 ? P.buf_width[o.res] : 0;
+        g.M = h->rows_cap; g.N = o.N;
+        char err[256] = "";
+        h->lnp[i] = ln_plan_create(g, h->rows_cap, err, sizeof err);
+        if (!h->lnp[i]) return fail(DS_ERR_CUDA, "tcgen05 GEMM+LayerNorm plan for op '%s' failed: %s", o.name.c_str(), err);
+        continue;
+      }
       g.gn = gemm_variant(h, o);
       g.n_obj = n_obj;
       if (o.kind == OP_GEMM_GN) {
@@ -378,6 +402,7 @@ extern "C" int ds_commit_weights(ds_handle* h) {
   std::vector<char> gnt_w(P.wmats.size(), 0);       // weight matrices consumed by fused GroupNorm ops
   std::vector<char> row_major_w(P.wmats.size(), 0);
   for (const Op& o : P.ops) {
+    if (o.kind == OP_GEMM_LN) { row_major_w[o.w] = 1; continue; }
     if (o.kind != OP_GEMM && o.kind != OP_GEMM_GN) continue;
     if (gemm_variant(h, o) >= 2) gnt_w[o.w] = 1;
     else row_major_w[o.w] = 1;

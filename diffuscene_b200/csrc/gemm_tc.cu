@@ -32,16 +32,12 @@
 #include <string.h>
 
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace ds {
 
-static constexpr int BM = 128;
-static constexpr int BK = 64;
 static constexpr int EPI_WARPS = 8;
 static constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
-static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
-static constexpr uint64_t WAIT_TIMEOUT_CYCLES = 4000000000ull;   // ~2 s: a protocol bug traps instead of hanging
-
 struct TcEpi {
   const float* bias;
   bf16* d; int ldd;
@@ -65,158 +61,7 @@ struct TcEpi {
 // trace slots: 0 producer wait-empty, 1 producer total, 2 mma wait-tmem-empty, 3 mma wait-full, 4 mma total,
 //              5 epilogue(warp 2) wait-tmem-full, 6 epilogue total, 7 tiles processed
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a mis-programmed pipeline traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = clock64();
-  unsigned int spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > WAIT_TIMEOUT_CYCLES) {     // clock read once per 1024 polls
-      if (err_flag) atomicExch(err_flag, code);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
-                                               uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%2, %3}], [%4], %5;"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-               ::"l"(map), "r"(c0), "r"(c1), "r"(src)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
-__host__ __device__ constexpr uint64_t umma_desc_hi_sw128() {
-  return ((uint64_t)1 << 16)                      // leading byte offset (unused for swizzled K-major)
-         | ((uint64_t)(1024 >> 4) << 32)          // stride byte offset between 8-row groups
-         | ((uint64_t)1 << 46)                    // descriptor version (Blackwell)
-         | ((uint64_t)2 << 61);                   // SWIZZLE_128B
-}
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint64_t hi) {
-  return hi | (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address in 16-byte units
-}
-// D(tmem, fp32) (+)= A(smem, bf16) * B(smem, bf16)^T, M = 128, N from the instruction descriptor, K = 16
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(bar), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// x * sigmoid(x) = h + h * tanh(h), h = x / 2  (one MUFU op; |rel err| ~ 2^-11, below the bf16 output ulp)
-__device__ __forceinline__ float silu_from_half(float h) {      // argument is x / 2
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
-__device__ __forceinline__ float silu_tanh(float x) { return silu_from_half(0.5f * x); }
-
-// GELU in its tanh form (max |deviation| from the erf form ~3e-4, below the bf16 output ulp for |x| > 0.1):
-// 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  -- throughput mode only; the fp32 parity path uses erff
-__device__ __forceinline__ float gelu_tanh(float x) {
-  float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f), t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  float h = 0.5f * x;
-  return fmaf(h, t, h);
-}
 
 template <int BN, bool GN>
 struct TcCfg {
@@ -781,8 +626,8 @@ struct GntCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int CHAN_MAX_N = 512;
   static constexpr int CHAN_BYTES = CHAN_MAX_N * 20;            // bias | (gamma, beta) | uniform FiLM
-  static constexpr int RED_BYTES = SC * 128 * 8;                // (sum, sum of squares) per (scene, channel)
-  static constexpr int STAT_BYTES = SC * 2 * 8;                 // (mean, rstd) per (scene, group of the tile)
+  static constexpr int RED_BYTES = 2 * 8 * 4 * 4 * 4;           // [tile parity][warp pair][scene][S, SS of both warps] floats
+  static constexpr int STAT_BYTES = 0;
   // a scene is moved as NPAIR (token 2i, token 2i + 1) pairs; an odd scene pads its last pair with a dummy token
   static constexpr int NPAIR = (NOBJ + 1) / 2;
   static constexpr int NG4 = NPAIR / 4;                         // full ldmatrix / stmatrix .x4 groups (8 tokens each)
@@ -886,8 +731,9 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   float* const bias_s = reinterpret_cast<float*>(base_ptr + Cfg::SCRATCH_OFF);
   float2* const gb_s = reinterpret_cast<float2*>(base_ptr + Cfg::SCRATCH_OFF + Cfg::CHAN_MAX_N * 4);
   float2* const film_u = reinterpret_cast<float2*>(base_ptr + Cfg::SCRATCH_OFF + Cfg::CHAN_MAX_N * 12);
-  float2* const red = reinterpret_cast<float2*>(base_ptr + Cfg::RED_OFF);
-  float2* const stat = reinterpret_cast<float2*>(base_ptr + Cfg::STAT_OFF);
+  // GroupNorm partial sums exchanged between the TWO warps that share a (scene range, group):
+  // [tile parity][pair 0..7][scene 0..3][S_q0, SS_q0, S_q1, SS_q1]
+  float* const red2 = reinterpret_cast<float*>(base_ptr + Cfg::RED_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -945,7 +791,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         const int m0 = tt * Cfg::TOK;
         for (int kb = 0; kb < kblocks; ++kb) {
           unsigned long long t0 = epi.trace ? clock64() : 0;
-          mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
+          mbar_wait<32>(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
@@ -976,13 +822,13 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
       unsigned long long tw_te = 0, tw_f = 0, tstart = clock64();
       for (int tile = unit0; tile < total; tile += unit_step) {
         unsigned long long t0 = epi.trace ? clock64() : 0;
-        mbar_wait(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
+        mbar_wait<32>(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
         if (epi.trace) tw_te += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(ab * Cfg::ACC_STRIDE);
         for (int kb = 0; kb < kblocks; ++kb) {
           t0 = epi.trace ? clock64() : 0;
-          mbar_wait(full_bar(stage), phase, err_flag, 3);
+          mbar_wait<32>(full_bar(stage), phase, err_flag, 3);
           if (epi.trace) tw_f += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
@@ -1011,7 +857,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     const int part = (warp - 2) >> 2;                // which scenes of the tile
     const int etid = threadIdx.x - 64;
     const int chl = 32 * q + 8 * (lane & 3) + (lane >> 2);      // channel (inside the tile) on this thread's lane
-    const int gq = q >> 1;                                       // GroupNorm group of the tile (64 channels each)
+    const int pr = part * 2 + (q >> 1);                         // warp pair sharing a (scene range, 64-channel group)
     const bool film_uni = epi.film.mode == FILM_TIME && epi.film_uniform;
     const bool per_scene_t = epi.film.mode == FILM_TIME && !film_uni;
     const float* fr_u = film_uni ? epi.film.base + (int64_t)__ldg(epi.film.t) * epi.film.row_stride : nullptr;
@@ -1055,7 +901,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
       constexpr int FM = decltype(fm_tag)::value;
       constexpr bool RES = decltype(res_tag)::value;
       int cg = unit0 % cgn, tt = unit0 / cgn;
-      for (int tile = unit0; tile < total; tile += unit_step) {
+      int tile_par = 0;
+      for (int tile = unit0; tile < total; tile += unit_step, tile_par ^= 1) {
         const int ct = cg * int(cs) + int(crank);
         const int ch = ct * BM + chl;
         float bias;
@@ -1101,6 +948,23 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         };
         if constexpr (RES) {
           if (0 < n_live) fetch_res();
+          // Pull the NEXT tile's residual rows of this warp towards L2 now, a whole tile time ahead of their use: the
+          // per-scene fetches in pass 2 then hit L2 instead of waiting on HBM (the largest single stall of this
+          // kernel in the round-1 profile).  The very first tile of a CTA prefetches its own rows as well.
+          auto prefetch_rows = [&](int p_tt, int p_ct) {
+            const int p_scene0 = p_tt * Cfg::SC + s_begin;
+            const char* pp = reinterpret_cast<const char*>(epi.res + ((int64_t)p_scene0 * NOBJ + lane) * epi.ldres + p_ct * BM + 32 * q);
+            const int rows_left = epi.M - p_scene0 * NOBJ;
+            if (lane < Cfg::SPP * NOBJ && lane < rows_left) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+            if (lane + 32 < Cfg::SPP * NOBJ && lane + 32 < rows_left)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (int64_t)32 * epi.ldres * 2));
+          };
+          if (tile == unit0) prefetch_rows(tt, ct);
+          if (tile + unit_step < total) {
+            int ncg = cg + step_cg, ntt = tt + step_tt;
+            if (ncg >= cgn) { ncg -= cgn; ++ntt; }
+            prefetch_rows(ntt, ncg * int(cs) + int(crank));
+          }
         }
         unsigned long long t0 = epi.trace ? clock64() : 0;
         mbar_wait(tfull_bar(ab), aphase, err_flag, 4);
@@ -1108,11 +972,18 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * Cfg::ACC_STRIDE + s_begin * NOBJ);
 
-        // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
+        // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens (bias folded analytically),
+        //      reduced over the 32 channels of this warp with a butterfly reduce-scatter (9 shuffles for the 8 values
+        //      {sum, sum of squares} x <= 4 scenes), then exchanged with the ONE other warp that holds the rest of the
+        //      64-channel group through shared memory and a 64-thread named barrier: no CTA-wide barrier, the 8 warp
+        //      pairs of a tile run decoupled from each other
+        float* const r2 = red2 + ((tile_par * 8 + pr) * 16);
         if constexpr (FM != 4) {
+          float v8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v8[i] = 0.f;
           uint32_t va[NOBJ];
           tmem_ld_scene_issue(taddr, va);
-          float2* rdst = red + s_begin * 128 + 32 * q + lane;
 #pragma unroll
           for (int si = 0; si < Cfg::SPP; ++si) {
             tmem_ld_scene_wait(va);
@@ -1126,40 +997,40 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
               s1 += v[j];
               s2 = fmaf(v[j], v[j], s2);
             }
-            const float S = fmaf(float(NOBJ), bias, s1);
-            const float SS = fmaf(bias, fmaf(float(NOBJ), bias, 2.0f * s1), s2);
-            rdst[si * 128] = make_float2(S, SS);
+            v8[si] = fmaf(float(NOBJ), bias, s1);
+            v8[4 + si] = fmaf(bias, fmaf(float(NOBJ), bias, 2.0f * s1), s2);
           }
-        }
-        if constexpr (FM != 4) epi_bar();
-        if (FM != 4 && etid < Cfg::SC * 2 * 8) {                  // 8 threads per (scene, group): whole warps by construction
-          const int pid = etid >> 3, sub = etid & 7;
-          const float2* rsrc = red + (pid >> 1) * 128 + (pid & 1) * 64 + sub;
-          float s = 0.f, ss = 0.f;
+          {
+            const bool up = (lane & 16) != 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 p2 = rsrc[8 * i];
-            s += p2.x;
-            ss += p2.y;
+            for (int i = 0; i < 4; ++i) {
+              const float send = up ? v8[i] : v8[i + 4], keep = up ? v8[i + 4] : v8[i];
+              v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
           }
+          {
+            const bool up = (lane & 8) != 0;
 #pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            for (int i = 0; i < 2; ++i) {
+              const float send = up ? v8[i] : v8[i + 2], keep = up ? v8[i + 2] : v8[i];
+              v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
           }
-          if (sub == 0) {
-            const float inv = 1.0f / float(NOBJ * 64);
-            const float mean = s * inv;
-            const float var = fmaxf(ss * inv - mean * mean, 0.f);
-            stat[pid] = make_float2(mean, rsqrtf(var + 1e-5f));
+          {
+            const bool up = (lane & 4) != 0;
+            const float send = up ? v8[0] : v8[1], keep = up ? v8[1] : v8[0];
+            v8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
           }
+          v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
+          v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
+          // lane l holds the warp total of value l >> 2: scene (l >> 2) & 3, sum (l < 16) or sum of squares (l >= 16)
+          if ((lane & 3) == 0) r2[((lane >> 2) & 3) * 4 + (q & 1) * 2 + (lane >> 4)] = v8[0];
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + pr) : "memory");
         }
-        if constexpr (FM != 4) epi_bar();
 
         // ---- pass 2: normalise + FiLM + SiLU (+ residual) per scene, transposed store through the staging blocks
         uint32_t va[NOBJ];
         tmem_ld_scene_issue(taddr, va);
-        const float2* stp = stat + s_begin * 2 + gq;
 #pragma unroll 1
         for (int si = 0; si < Cfg::SPP; ++si) {
           const bool live = si < n_live;
@@ -1174,9 +1045,12 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           }
           float a = 1.0f, b = bias;
           if constexpr (FM != 4) {
-            const float2 st = stp[2 * si];
-            a = st.y * Ps;
-            b = fmaf(bias - st.x, a, Qs);
+            const float4 t4 = reinterpret_cast<const float4*>(r2)[si];
+            const float inv = 1.0f / float(NOBJ * 64);
+            const float mean = (t4.x + t4.z) * inv;
+            const float var = fmaxf((t4.y + t4.w) * inv - mean * mean, 0.f);
+            a = rsqrtf(var + 1e-5f) * Ps;
+            b = fmaf(bias - mean, a, Qs);
           }
           tmem_ld_scene_wait(va);
           float y[2 * Cfg::PKN];                      // tokens >= NOBJ: padding of the last pair(s), never stored
@@ -1596,5 +1470,16 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
 }
 
 int tc_error_flag() { return g_err_flag ? *g_err_flag : 0; }
+// shared with the other tcgen05 kernels of the library (gemm_ln.cu)
+bool tc_encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
+                  uint32_t box_rows, char* err, int err_len) {
+  return encode_2d(map, base, inner, rows, pitch_elems, box_rows, err, err_len);
+}
+int* tc_error_flag_dev() {
+  int* fd = nullptr;
+  cudaHostGetDevicePointer((void**)&fd, g_err_flag, 0);
+  return fd;
+}
+int tc_num_sms() { return g_num_sms; }
 
 }  // namespace ds

@@ -132,6 +132,12 @@ bool tc_runtime_available(char* err, int err_len);
 bool tc_gnt_supported(int n_obj, int N);
 // GemmArgs.gn == 3: the same kernel as a plain GEMM (bias, activation, residual); same weight row order
 bool tc_gnt_plain_supported(int n_obj, int N);
+// fused GEMM + channel LayerNorm (+ residual) for K <= 128, N = 512 (gemm_ln.cu): GemmArgs.gamma = LayerNorm gain
+struct LnGemmPlan;
+bool ln_gemm_supported(int N, int K);
+LnGemmPlan* ln_plan_create(const GemmArgs& g, int rows_capacity, char* err, int err_len);
+void ln_plan_destroy(LnGemmPlan* p);
+int launch_gemm_ln(const LnGemmPlan* p, int M, cudaStream_t s);
 inline int tc_gnt_row(int stored_row) { const int l = stored_row & 31; return (stored_row & ~31) + 8 * (l & 3) + (l >> 2); }
 
 }  // namespace ds

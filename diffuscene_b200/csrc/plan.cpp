@@ -12,6 +12,7 @@ struct Builder {
   Plan* p;
   bool no_reuse;
   bool fuse = false;
+  bool fuse_ln = false;     // to_out + LayerNorm + residual of the attention wrappers as one op
   std::vector<int> refs;
   std::map<int, std::vector<int>> free_by_width;
   int C;
@@ -167,6 +168,27 @@ struct Builder {
     p->ops.push_back(o);
   }
 
+  // to_out = Sequential(Conv1d(hidden, dim, 1), LayerNorm(dim)) followed by the Residual add (denoise_net.py:214-217,
+  // 234-235, 39-45): one GEMM with the LayerNorm epilogue at fuse_level >= 4, a GEMM and a LayerNorm op otherwise
+  int to_out_ln(const std::string& name, int o, int x, int H) {
+    int out = new_buf(C);
+    if (fuse_ln) {
+      Op op;
+      op.kind = OP_GEMM_LN; op.name = name; op.in0 = full(o); op.out = out; op.N = C; op.res = x;
+      op.w = wsingle(name + ".fn.fn.to_out.0.weight", C, H);
+      op.b = vsingle(name + ".fn.fn.to_out.0.bias", C);
+      op.gamma = vsingle(name + ".fn.fn.to_out.1.g", C);
+      p->ops.push_back(op);
+      return out;
+    }
+    int y = new_buf(C);
+    gemm(name + ".to_out", full(o), Slice(), wsingle(name + ".fn.fn.to_out.0.weight", C, H),
+         vsingle(name + ".fn.fn.to_out.0.bias", C), C, 0, -1, y, 0);
+    ln(name, y, out, vsingle(name + ".fn.fn.to_out.1.g", C), x);
+    release(y);
+    return out;
+  }
+
   // Residual(PreNorm(LinearAttention)) (denoise_net.py:208-235) / Attention for the mid block (:237-259)
   int self_attn(const std::string& name, int x, bool softmax_kind) {
     const int H = 128;
@@ -184,19 +206,15 @@ struct Builder {
       p->ops.push_back(op);
     }
     release(qkv);
-    int out = new_buf(C);
+    int out;
     if (softmax_kind) {
+      out = new_buf(C);
       gemm(name, full(o), Slice(), wsingle(name + ".fn.fn.to_out.weight", C, H), vsingle(name + ".fn.fn.to_out.bias", C),
            C, 0, x, out, 0);
-      release(o);
     } else {
-      int y = new_buf(C);
-      gemm(name + ".to_out", full(o), Slice(), wsingle(name + ".fn.fn.to_out.0.weight", C, H),
-           vsingle(name + ".fn.fn.to_out.0.bias", C), C, 0, -1, y, 0);
-      release(o);
-      ln(name, y, out, vsingle(name + ".fn.fn.to_out.1.g", C), x);
-      release(y);
+      out = to_out_ln(name, o, x, H);
     }
+    release(o);
     return out;
   }
 
@@ -218,13 +236,8 @@ struct Builder {
       p->ops.push_back(op);
     }
     release(q);
-    int y = new_buf(C);
-    gemm(name + ".to_out", full(o), Slice(), wsingle(name + ".fn.fn.to_out.0.weight", C, H),
-         vsingle(name + ".fn.fn.to_out.0.bias", C), C, 0, -1, y, 0);
+    int out = to_out_ln(name, o, x, H);
     release(o);
-    int out = new_buf(C);
-    ln(name, y, out, vsingle(name + ".fn.fn.to_out.1.g", C), x);
-    release(y);
     return out;
   }
 };
@@ -281,6 +294,8 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
   b.C = C;
   b.fuse = cfg.fuse_level >= 1 && cfg.precision == DS_PREC_BF16 && cfg.gemm_backend != DS_GEMM_SIMT && C % 256 == 0 && C <= 512 &&
            128 / cfg.num_objects <= 10;   // the fused epilogue's coefficient table holds <= 10 scenes per tile
+
+  b.fuse_ln = b.fuse && cfg.fuse_level >= 4 && C == 512;
 
   // ---- input + encoder ----
   int xin = b.new_buf(P.kin_pad);
@@ -431,7 +446,7 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
 }
 
 std::string describe_plan(const Plan& p) {
-  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN", "GEMM_GN"};
+  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN", "GEMM_GN", "GEMM_LN"};
   std::ostringstream os;
   os << "plan: C=" << p.C << " d=" << p.d << " kin_pad=" << p.kin_pad << " dpad=" << p.dpad << " buffers="
      << p.buf_width.size() << " ops=" << p.ops.size() << " time_blocks=" << p.time_blocks.size()
@@ -439,7 +454,7 @@ std::string describe_plan(const Plan& p) {
   for (size_t i = 0; i < p.ops.size(); ++i) {
     const Op& o = p.ops[i];
     os << i << " " << kinds[o.kind] << " " << o.name;
-    if (o.kind == OP_GEMM || o.kind == OP_GEMM_GN) {
+    if (o.kind == OP_GEMM || o.kind == OP_GEMM_GN || o.kind == OP_GEMM_LN) {
       os << " K=" << (o.in0.k + o.in1.k) << " N=" << o.N << " a0=b" << o.in0.buf << "[" << o.in0.col << ":" << o.in0.k
          << "]";
       if (o.in1.buf >= 0) os << " a1=b" << o.in1.buf;

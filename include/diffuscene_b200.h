@@ -71,7 +71,9 @@ typedef struct ds_config {
   int32_t device;           /* CUDA device ordinal                                     */
   int32_t fuse_level;       /* 0: one kernel per op; 1: fused GEMM epilogues; 2: + the
                                channels-on-lanes conv+GroupNorm GEMM where supported;
-                               3: + epilogue-bound plain GEMMs on that kernel           */
+                               3: + epilogue-bound plain GEMMs on that kernel;
+                               4: + to_out + LayerNorm + residual of the attention wrappers
+                                  as one GEMM with a LayerNorm epilogue                  */
   int32_t reserved[7];
 } ds_config;
 

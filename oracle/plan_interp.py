@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .unet1d_ref import sinusoidal_embedding
 
-OP_PACK, OP_GEMM, OP_GN, OP_LN, OP_LINATTN, OP_ATTN, OP_XATTN, OP_GEMM_GN = range(8)
+OP_PACK, OP_GEMM, OP_GN, OP_LN, OP_LINATTN, OP_ATTN, OP_XATTN, OP_GEMM_GN, OP_GEMM_LN = range(9)
 
 
 def _r(x, on):
@@ -79,7 +79,7 @@ def run_plan(plan: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.
             bufs[op["out"]] = _r(out, bf)
             continue
         i0 = op["in0"]
-        if k == OP_GEMM or k == OP_GEMM_GN:
+        if k == OP_GEMM or k == OP_GEMM_GN or k == OP_GEMM_LN:
             a = bufs[i0["buf"]][:, i0["col"]:i0["col"] + i0["k"]]
             if op["in1"]["buf"] >= 0:
                 i1 = op["in1"]
@@ -99,6 +99,13 @@ def run_plan(plan: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.
                 f = film_c[op["film_blk"]].reshape(B, N, 2 * C)
                 y = y * (f[..., :C] + 1) + f[..., C:]
             y = F.silu(y).reshape(M, C)
+            if op["res"] >= 0:
+                y = y + bufs[op["res"]]
+            bufs[op["out"]] = _r(y, bf)
+        elif k == OP_GEMM_LN:    # the projection stays in fp32 (TMEM) through the LayerNorm epilogue
+            mean = y.mean(dim=1, keepdim=True)
+            var = y.var(dim=1, unbiased=False, keepdim=True)
+            y = (y - mean) * torch.rsqrt(var + 1e-5) * vecs[op["gamma"]]
             if op["res"] >= 0:
                 y = y + bufs[op["res"]]
             bufs[op["out"]] = _r(y, bf)

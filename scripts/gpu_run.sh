@@ -4,6 +4,8 @@
 #   bench [bench args]      one bench.py run, JSON line -> gpurun_out/<tag>_bench.json
 #   ops   [bench args]      per-op device-time table of one step program -> gpurun_out/<tag>_per_op_us.txt
 #   launches [bench args]   ncu launch list (time + DRAM bytes) of a short bench -> gpurun_out/<tag>_launches.csv
+#   probe                   isolated GEMM timings + numeric checks (tests/gpu_trace_gemm.py)
+#   py <script> [args]      any python script
 #   full <kernel-regex> [skip] [count]   one `ncu --set full` capture -> gpurun_out/<tag>_<...>.ncu-rep
 # Several tasks can be chained with "--":  gpu_run.sh r2 tests -- bench --steps 2
 cd "$(dirname "$0")/.."
@@ -33,6 +35,10 @@ run_task() {
         -o gpurun_out/${TAG}_$(echo $k | tr -c 'a-zA-Z0-9\n' _)_full -f python bench.py --steps 1 --warmup 1 --timesteps 2 \
         --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_full.log 2>&1
       tail -2 gpurun_out/${TAG}_full.log | cut -c1-300; ls -la gpurun_out/${TAG}_*.ncu-rep ;;
+    probe)
+      GNT_ONLY=1 timeout 600 python tests/gpu_trace_gemm.py 2>&1 | tee gpurun_out/${TAG}_gemm_probe.txt | grep -v "^   prod_wait" | tail -60 ;;
+    py)
+      timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
   esac
 }
