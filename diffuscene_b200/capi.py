@@ -22,7 +22,7 @@ class DsConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "dim", "channels", "seperate_all", "objectness_dim", "class_dim", "translation_dim", "size_dim",
         "angle_dim", "objfeat_dim", "cond_dim", "text_condition", "text_dim", "n_stages", "num_objects",
-        "num_timesteps", "precision", "gemm_backend", "device", "fuse_level")] + [("reserved", C.c_int32 * 7)]
+        "num_timesteps", "precision", "gemm_backend", "device", "fuse_level", "train")] + [("reserved", C.c_int32 * 6)]
 
 
 class DsSchedule(C.Structure):
@@ -77,6 +77,12 @@ def load(rebuild: bool = False):
         "ds_p_sample_step": (C.c_int, [H, p, p, p, C.c_int32, p, C.c_int32, p]),
         "ds_q_sample": (C.c_int, [H, p, p, p, p, C.c_int32, p]),
         "ds_p_losses": (C.c_int, [H, p, p, p, C.c_int32, C.c_int32, p, p, p, C.c_int32, p]),
+        "ds_train_param_count": (C.c_int64, [H]),
+        "ds_train_step": (C.c_int, [H, p, p, p, p, p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, p, C.c_float, p, p, p, p,
+                                    C.c_int32, p]),
+        "ds_sumsq": (C.c_int, [p, C.c_int64, p, p]),
+        "ds_adam_step": (C.c_int, [p, p, p, p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, p,
+                                   C.c_float, p]),
         "ds_retrieve_objects": (C.c_int, [p, C.c_int32, p, p, C.c_int32, C.c_int32, p, p, p, C.c_int32, C.c_int32, p, p]),
         "ds_plan_describe": (C.c_int, [C.POINTER(DsConfig), C.c_char_p, C.c_int64]),
         "ds_plan_export_json": (C.c_int, [C.POINTER(DsConfig), C.c_int32, C.c_char_p, C.c_int64]),
@@ -101,6 +107,7 @@ EXPORTED = ["ds_create", "ds_destroy", "ds_last_error", "ds_version", "ds_load_w
             "ds_expected_weight_count", "ds_expected_weight", "ds_set_schedule", "ds_set_context",
             "ds_set_context_cross", "ds_denoise_forward", "ds_denoise_forward_host", "ds_sample_loop",
             "ds_sample_loop_host", "ds_traj_count", "ds_p_sample_step", "ds_q_sample", "ds_p_losses", "ds_retrieve_objects",
+            "ds_train_param_count", "ds_train_step", "ds_sumsq", "ds_adam_step",
             "ds_plan_describe", "ds_plan_export_json", "ds_enable_taps", "ds_read_tap", "ds_launch_count", "ds_graph_build_count", "ds_gnt_weight_row", "ds_profile_ops",
             "ds_test_gemm_bf16", "ds_test_gemm_trace"]
 
@@ -118,7 +125,7 @@ def check(rc: int):
 
 
 def make_config(spec, num_objects: int, num_timesteps: int, precision: int = DS_PREC_BF16,
-                gemm_backend: int = DS_GEMM_AUTO, device: int = 0, fuse_level: int = 0) -> DsConfig:
+                gemm_backend: int = DS_GEMM_AUTO, device: int = 0, fuse_level: int = 0, train: int = 0) -> DsConfig:
     """DsConfig from a diffuscene_b200.weights.NetSpec."""
     c = DsConfig()
     c.dim, c.channels, c.seperate_all = spec.dim, spec.channels, int(spec.seperate_all)
@@ -128,6 +135,7 @@ def make_config(spec, num_objects: int, num_timesteps: int, precision: int = DS_
     c.text_condition, c.text_dim = int(spec.text_condition), spec.text_dim
     c.n_stages, c.num_objects, c.num_timesteps = spec.n_stages, num_objects, num_timesteps
     c.precision, c.gemm_backend, c.device, c.fuse_level = precision, gemm_backend, device, fuse_level
+    c.train = int(train)
     return c
 
 

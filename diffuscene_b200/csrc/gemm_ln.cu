@@ -112,7 +112,7 @@ k_gemm_ln(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait<32>(empty_bar(stage), phase ^ 1u, err_flag, 11);
+          mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 11);
           mbar_expect_tx(full_bar(stage), A_BYTES);
           tma_load_2d(base + LN_A_OFF + stage * A_BYTES, &tm_a, kb * BK, tile * BM, full_bar(stage));
           if (++stage == LN_STAGES) { stage = 0; phase ^= 1u; }
@@ -121,15 +121,15 @@ k_gemm_ln(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      mbar_wait<32>(wfull_bar, 0, err_flag, 12);
+      mbar_wait(wfull_bar, 0, err_flag, 12);
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait<32>(tempty_bar, tphase ^ 1u, err_flag, 13);      // the epilogue has drained the accumulator
+        mbar_wait(tempty_bar, tphase ^ 1u, err_flag, 13);      // the epilogue has drained the accumulator
         tphase ^= 1u;
         tc_fence_after();
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait<32>(full_bar(stage), phase, err_flag, 14);
+          mbar_wait(full_bar(stage), phase, err_flag, 14);
           tc_fence_after();
           const uint64_t adesc = umma_desc(base + LN_A_OFF + stage * A_BYTES, epi.desc_hi);
           const uint64_t b0 = umma_desc(base + uint32_t(kb * LN_C * BK * 2), epi.desc_hi);

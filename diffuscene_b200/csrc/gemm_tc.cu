@@ -56,6 +56,7 @@ struct TcEpi {
   FilmRef film;
   int film_uniform;      // FILM_TIME only: t[] holds one value for the whole launch (sampling loop)
   int plain;             // channels-on-lanes kernel without GroupNorm: bias, activation, residual only
+  int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
 };
 // trace slots: 0 producer wait-empty, 1 producer total, 2 mma wait-tmem-empty, 3 mma wait-full, 4 mma total,
@@ -610,7 +611,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 // lanes of a warp to hold the channels in the order 8 (lane % 4) + lane / 4.  The host stores the weight rows of
 // these convs in exactly that order inside every block of 32 (ds_commit_weights), so the shuffle costs nothing.
 // GroupNorm statistics: per-(scene, channel) partials -> shared memory -> 8 threads per (scene, group) reduce.
-template <int NOBJ>
+template <int NOBJ, bool PAIR = true>
 struct GntCfg {
   static constexpr int SC = (NOBJ == 12) ? 16 : 256 / NOBJ;   // scenes per tile (16 for N = 12, 12 for N = 21)
   static constexpr int TOK = SC * NOBJ;                         // tokens per tile (192 / 252)
@@ -626,8 +627,10 @@ struct GntCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int CHAN_MAX_N = 512;
   static constexpr int CHAN_BYTES = CHAN_MAX_N * 20;            // bias | (gamma, beta) | uniform FiLM
-  static constexpr int RED_BYTES = 2 * 8 * 4 * 4 * 4;           // [tile parity][warp pair][scene][S, SS of both warps] floats
-  static constexpr int STAT_BYTES = 0;
+  // PAIR: [tile parity][warp pair][scene][S, SS of both warps] floats;  else (sum, sum of squares) per (scene, channel)
+  // and (mean, rstd) per (scene, group of the tile), reduced behind two CTA-wide barriers
+  static constexpr int RED_BYTES = PAIR ? 2 * 8 * 4 * 4 * 4 : SC * 128 * 8;
+  static constexpr int STAT_BYTES = PAIR ? 0 : SC * 2 * 8;
   // a scene is moved as NPAIR (token 2i, token 2i + 1) pairs; an odd scene pads its last pair with a dummy token
   static constexpr int NPAIR = (NOBJ + 1) / 2;
   static constexpr int NG4 = NPAIR / 4;                         // full ldmatrix / stmatrix .x4 groups (8 tokens each)
@@ -712,12 +715,12 @@ __device__ __forceinline__ void stsm_x2_t(uint32_t addr, uint32_t r0, uint32_t r
   asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
 }
 
-template <int NOBJ>
+template <int NOBJ, bool PAIR>
 // 18 warps = 5 on the fullest SM sub-partition: 16384 / (5 * 32) = 102 registers per thread at most
 __global__ void __maxnreg__(96)
 k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x0,
            const __grid_constant__ CUtensorMap tm_x1, TcEpi epi, int* err_flag) {
-  using Cfg = GntCfg<NOBJ>;
+  using Cfg = GntCfg<NOBJ, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -734,6 +737,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   // GroupNorm partial sums exchanged between the TWO warps that share a (scene range, group):
   // [tile parity][pair 0..7][scene 0..3][S_q0, SS_q0, S_q1, SS_q1]
   float* const red2 = reinterpret_cast<float*>(base_ptr + Cfg::RED_OFF);
+  float2* const red = reinterpret_cast<float2*>(base_ptr + Cfg::RED_OFF);        // !PAIR layout
+  float2* const stat = reinterpret_cast<float2*>(base_ptr + Cfg::STAT_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -791,7 +796,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         const int m0 = tt * Cfg::TOK;
         for (int kb = 0; kb < kblocks; ++kb) {
           unsigned long long t0 = epi.trace ? clock64() : 0;
-          mbar_wait<32>(empty_bar(stage), phase ^ 1u, err_flag, 1);
+          mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
@@ -822,13 +827,13 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
       unsigned long long tw_te = 0, tw_f = 0, tstart = clock64();
       for (int tile = unit0; tile < total; tile += unit_step) {
         unsigned long long t0 = epi.trace ? clock64() : 0;
-        mbar_wait<32>(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
+        mbar_wait(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
         if (epi.trace) tw_te += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(ab * Cfg::ACC_STRIDE);
         for (int kb = 0; kb < kblocks; ++kb) {
           t0 = epi.trace ? clock64() : 0;
-          mbar_wait<32>(full_bar(stage), phase, err_flag, 3);
+          mbar_wait(full_bar(stage), phase, err_flag, 3);
           if (epi.trace) tw_f += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
@@ -959,8 +964,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             if (lane + 32 < Cfg::SPP * NOBJ && lane + 32 < rows_left)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (int64_t)32 * epi.ldres * 2));
           };
-          if (tile == unit0) prefetch_rows(tt, ct);
-          if (tile + unit_step < total) {
+          if (epi.res_prefetch && tile == unit0) prefetch_rows(tt, ct);
+          if (epi.res_prefetch && tile + unit_step < total) {
             int ncg = cg + step_cg, ntt = tt + step_tt;
             if (ncg >= cgn) { ncg -= cgn; ++ntt; }
             prefetch_rows(ntt, ncg * int(cs) + int(crank));
@@ -972,12 +977,13 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ab * Cfg::ACC_STRIDE + s_begin * NOBJ);
 
+        float* const r2 = red2 + ((tile_par * 8 + pr) * 16);
+        if constexpr (PAIR) {
         // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens (bias folded analytically),
         //      reduced over the 32 channels of this warp with a butterfly reduce-scatter (9 shuffles for the 8 values
         //      {sum, sum of squares} x <= 4 scenes), then exchanged with the ONE other warp that holds the rest of the
         //      64-channel group through shared memory and a 64-thread named barrier: no CTA-wide barrier, the 8 warp
         //      pairs of a tile run decoupled from each other
-        float* const r2 = red2 + ((tile_par * 8 + pr) * 16);
         if constexpr (FM != 4) {
           float v8[8];
 #pragma unroll
@@ -1028,6 +1034,56 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           asm volatile("bar.sync %0, 64;" ::"r"(2 + pr) : "memory");
         }
 
+        } else {
+        // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
+        if constexpr (FM != 4) {
+          uint32_t va[NOBJ];
+          tmem_ld_scene_issue(taddr, va);
+          float2* rdst = red + s_begin * 128 + 32 * q + lane;
+#pragma unroll
+          for (int si = 0; si < Cfg::SPP; ++si) {
+            tmem_ld_scene_wait(va);
+            float v[NOBJ];
+#pragma unroll
+            for (int j = 0; j < NOBJ; ++j) v[j] = __uint_as_float(va[j]);
+            if (si + 1 < Cfg::SPP) tmem_ld_scene_issue(taddr + uint32_t((si + 1) * NOBJ), va);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < NOBJ; ++j) {
+              s1 += v[j];
+              s2 = fmaf(v[j], v[j], s2);
+            }
+            const float S = fmaf(float(NOBJ), bias, s1);
+            const float SS = fmaf(bias, fmaf(float(NOBJ), bias, 2.0f * s1), s2);
+            rdst[si * 128] = make_float2(S, SS);
+          }
+        }
+        if constexpr (FM != 4) epi_bar();
+        if (FM != 4 && etid < Cfg::SC * 2 * 8) {                  // 8 threads per (scene, group): whole warps by construction
+          const int pid = etid >> 3, sub = etid & 7;
+          const float2* rsrc = red + (pid >> 1) * 128 + (pid & 1) * 64 + sub;
+          float s = 0.f, ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 p2 = rsrc[8 * i];
+            s += p2.x;
+            ss += p2.y;
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          }
+          if (sub == 0) {
+            const float inv = 1.0f / float(NOBJ * 64);
+            const float mean = s * inv;
+            const float var = fmaxf(ss * inv - mean * mean, 0.f);
+            stat[pid] = make_float2(mean, rsqrtf(var + 1e-5f));
+          }
+        }
+        if constexpr (FM != 4) epi_bar();
+
+        }
         // ---- pass 2: normalise + FiLM + SiLU (+ residual) per scene, transposed store through the staging blocks
         uint32_t va[NOBJ];
         tmem_ld_scene_issue(taddr, va);
@@ -1045,12 +1101,18 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           }
           float a = 1.0f, b = bias;
           if constexpr (FM != 4) {
-            const float4 t4 = reinterpret_cast<const float4*>(r2)[si];
-            const float inv = 1.0f / float(NOBJ * 64);
-            const float mean = (t4.x + t4.z) * inv;
-            const float var = fmaxf((t4.y + t4.w) * inv - mean * mean, 0.f);
-            a = rsqrtf(var + 1e-5f) * Ps;
-            b = fmaf(bias - mean, a, Qs);
+            if constexpr (PAIR) {
+              const float4 t4 = reinterpret_cast<const float4*>(r2)[si];
+              const float inv = 1.0f / float(NOBJ * 64);
+              const float mean = (t4.x + t4.z) * inv;
+              const float var = fmaxf((t4.y + t4.w) * inv - mean * mean, 0.f);
+              a = rsqrtf(var + 1e-5f) * Ps;
+              b = fmaf(bias - mean, a, Qs);
+            } else {
+              const float2 st = (stat + s_begin * 2 + (q >> 1))[2 * si];
+              a = st.y * Ps;
+              b = fmaf(bias - st.x, a, Qs);
+            }
           }
           tmem_ld_scene_wait(va);
           float y[2 * Cfg::PKN];                      // tokens >= NOBJ: padding of the last pair(s), never stored
@@ -1241,8 +1303,10 @@ bool tc_runtime_available(char* err, int err_len) {
   cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_gnt<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_gnt<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, false>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
   return true;
 }
@@ -1311,7 +1375,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     if (const char* e = getenv("DS_GNT_CLUSTER")) gnt_cs = atoi(e);
     if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
   }
-  const int gnt_un = g.n_obj == 21 ? GntCfg<21>::UN : GntCfg<12>::UN, gnt_tok = g.n_obj == 21 ? GntCfg<21>::TOK : GntCfg<12>::TOK;
+  const int gnt_un = g.n_obj == 21 ? GntCfg<21, true>::UN : GntCfg<12, true>::UN, gnt_tok = g.n_obj == 21 ? GntCfg<21, true>::TOK : GntCfg<12, true>::TOK;
   const uint32_t act_box = gnt ? uint32_t(gnt_un / gnt_cs) : uint32_t(BM);     // rows of one activation load
   bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, act_box, err, err_len);
   if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, act_box, err, err_len);
@@ -1350,6 +1414,11 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.beta = g.beta;
   p->epi.film = g.film;
   p->epi.plain = plain_t ? 1 : 0;
+  {
+    // measured (profiles/round2_gnt_ab.txt): the prefetch makes the residual variants 4-5 % SLOWER -- off by default
+    static const int pf = getenv("DS_GNT_PREFETCH") ? atoi(getenv("DS_GNT_PREFETCH")) : 0;
+    p->epi.res_prefetch = pf;
+  }
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
   if (const char* e = getenv("DS_TC_IDESC")) p->epi.idesc = (uint32_t)strtoul(e, nullptr, 16);
@@ -1406,11 +1475,11 @@ static bool gnt_nobj_ok(int n_obj) {
   return n_obj == 12 || (n_obj == 21 && allow21);
 }
 bool tc_gnt_plain_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0; }
-bool tc_gnt_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0 && N <= GntCfg<12>::CHAN_MAX_N; }
+bool tc_gnt_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0 && N <= GntCfg<12, true>::CHAN_MAX_N; }
 
-template <int NOBJ>
+template <int NOBJ, bool PAIR>
 static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cudaStream_t s) {
-  using Cfg = GntCfg<NOBJ>;
+  using Cfg = GntCfg<NOBJ, PAIR>;
   const int n_scenes = epi.M / NOBJ;
   const int cs = p->cluster;
   const int total = ((n_scenes + Cfg::SC - 1) / Cfg::SC) * (epi.N / BM / cs);      // work units per cluster
@@ -1441,14 +1510,14 @@ static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cuda
       cfg.numAttrs = na;
       cfg.gridDim = dim3(max_cl * cs);
       int n = 0;
-      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<NOBJ>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
+      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<NOBJ, PAIR>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
     }
     if (cached < max_cl) max_cl = cached;
   }
   cfg.attrs = na ? attr : nullptr;
   cfg.numAttrs = na;
   cfg.gridDim = dim3((total < max_cl ? total : max_cl) * cs);
-  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<NOBJ>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<NOBJ, PAIR>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
 }
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
@@ -1457,7 +1526,11 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   if (p->gnt) {
     int* fd = nullptr;
     cudaHostGetDevicePointer((void**)&fd, g_err_flag, 0);
-    return epi.n_obj == 21 ? launch_gnt<21>(p, epi, fd, s) : launch_gnt<12>(p, epi, fd, s);
+    // GroupNorm statistics exchange: 0 (default) two CTA-wide barriers, 1 warp-pair local (named 64-thread barriers);
+    // A/B on one box (profiles/round2_gnt_ab.txt): no difference (39.3 / 43.2 / 66.3 us vs 40.0 / 43.2 / 66.0 us)
+    static const int pair = getenv("DS_GNT_PAIR") ? atoi(getenv("DS_GNT_PAIR")) : 0;
+    if (pair) return epi.n_obj == 21 ? launch_gnt<21, true>(p, epi, fd, s) : launch_gnt<12, true>(p, epi, fd, s);
+    return epi.n_obj == 21 ? launch_gnt<21, false>(p, epi, fd, s) : launch_gnt<12, false>(p, epi, fd, s);
   }
   const int num_m = (M + epi.tile_rows - 1) / epi.tile_rows;
   const int total_ct = ((num_m + p->cluster - 1) / p->cluster) * (epi.N / p->bn);

@@ -13,6 +13,8 @@ struct Builder {
   bool no_reuse;
   bool fuse = false;
   bool fuse_ln = false;     // to_out + LayerNorm + residual of the attention wrappers as one op
+  bool train = false;       // activations as separate ops (the backward pass needs the pre-activation)
+  std::map<int, int> zbuf;  // train: output buffer -> buffer of the same width holding the pre-activations
   std::vector<int> refs;
   std::map<int, std::vector<int>> free_by_width;
   int C;
@@ -64,6 +66,16 @@ struct Builder {
   }
 
   void gemm(const std::string& name, Slice a0, Slice a1, int w, int b, int N, int act, int res, int out, int out_col) {
+    if (train && act != 0) {
+      if (!zbuf.count(out)) zbuf[out] = new_buf(p->buf_width[out]);
+      const int zb = zbuf[out];
+      gemm(name + ".pre", a0, a1, w, b, N, 0, -1, zb, out_col);
+      Op o;
+      o.kind = OP_ACT; o.name = name; o.in0 = Slice{zb, out_col, N}; o.out = out; o.out_col = out_col; o.N = N; o.act = act;
+      o.res = res;
+      p->ops.push_back(o);
+      return;
+    }
     Op o;
     o.kind = OP_GEMM; o.name = name; o.in0 = a0; o.in1 = a1; o.w = w; o.b = b; o.N = N; o.act = act; o.res = res;
     o.out = out; o.out_col = out_col;
@@ -292,7 +304,8 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
   b.p = &P;
   b.no_reuse = no_reuse;
   b.C = C;
-  b.fuse = cfg.fuse_level >= 1 && cfg.precision == DS_PREC_BF16 && cfg.gemm_backend != DS_GEMM_SIMT && C % 256 == 0 && C <= 512 &&
+  b.train = cfg.train != 0;
+  b.fuse = !b.train && cfg.fuse_level >= 1 && cfg.precision == DS_PREC_BF16 && cfg.gemm_backend != DS_GEMM_SIMT && C % 256 == 0 && C <= 512 &&
            128 / cfg.num_objects <= 10;   // the fused epilogue's coefficient table holds <= 10 scenes per tile
 
   b.fuse_ln = b.fuse && cfg.fuse_level >= 4 && C == 512;
@@ -446,7 +459,7 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
 }
 
 std::string describe_plan(const Plan& p) {
-  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN", "GEMM_GN", "GEMM_LN"};
+  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN", "GEMM_GN", "GEMM_LN", "ACT"};
   std::ostringstream os;
   os << "plan: C=" << p.C << " d=" << p.d << " kin_pad=" << p.kin_pad << " dpad=" << p.dpad << " buffers="
      << p.buf_width.size() << " ops=" << p.ops.size() << " time_blocks=" << p.time_blocks.size()

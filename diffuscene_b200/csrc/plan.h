@@ -27,6 +27,7 @@ enum OpKind {
   OP_XATTN,         // cross linear-attention apply (q [M,128] x precomputed text context)
   OP_GEMM_GN,       // GEMM with the GroupNorm + affine (+FiLM) + SiLU (+res) epilogue fused (tcgen05 only)
   OP_GEMM_LN,       // GEMM with the channel LayerNorm (gain `gamma`) (+res) epilogue fused (tcgen05 only, fuse_level >= 4)
+  OP_ACT,           // train mode only: out[:, out_col : out_col + N] = act(in0) (GELU / SiLU as their own op, pre-activation kept)
 };
 
 struct Slice { int buf = -1; int col = 0; int k = 0; };

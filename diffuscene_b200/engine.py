@@ -226,6 +226,35 @@ class DenoiserEngine:
                                         barr, _ptr(losses), _ptr(ld), B, self._stream()))
         return losses, {k: ld[i] for i, k in enumerate(LOSS_KEYS)}
 
+    # ---- native training ------------------------------------------------------------------------
+    def flat_layout(self, prefix: str = "diffusion.model.") -> Dict[str, tuple]:
+        """name -> (offset, numel) of every denoiser parameter inside the flat fp32 parameter / gradient buffers."""
+        out, off = {}, 0
+        for name, numel in self.expected_weights():
+            out[prefix + name] = (off, numel)
+            off += numel
+        return out
+
+    def train_step(self, flat_params: torch.Tensor, x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
+                   context: torch.Tensor, shared: bool, loss_separate: bool, loss_iou: bool,
+                   bounds: Optional[Sequence[float]] = None, flat_grads: Optional[torch.Tensor] = None,
+                   want_dcontext: bool = True, grad_scale: float = 1.0):
+        """Forward of p_losses + the native backward pass: (losses [B], loss dict, d(context) or None).
+        Gradients of every denoiser parameter land in `flat_grads` (flat_layout order)."""
+        assert flat_params.is_cuda and flat_params.dtype == torch.float32 and flat_params.is_contiguous()
+        x0, t, noise = x0.contiguous(), t.to(self.device).contiguous(), noise.contiguous()
+        ctx = context.detach().to(self.device, torch.float32).contiguous()
+        B = x0.shape[0]
+        losses = torch.empty(B, device=self.device, dtype=torch.float32)
+        ld = torch.empty(9, device=self.device, dtype=torch.float32)
+        dctx = torch.empty_like(ctx) if (want_dcontext and flat_grads is not None) else None
+        barr = None if bounds is None else (C.c_float * 12)(*[float(v) for v in bounds])
+        capi.check(self.lib.ds_train_step(self.h, _ptr(flat_params), _ptr(x0), _ptr(t), _ptr(noise), _ptr(ctx),
+                                          0 if shared else B, int(bool(shared)), int(loss_separate), int(loss_iou), barr,
+                                          float(grad_scale), _ptr(losses), _ptr(ld), _ptr(flat_grads), _ptr(dctx), B,
+                                          self._stream()))
+        return losses, {k: ld[i] for i, k in enumerate(LOSS_KEYS)}, dctx
+
     # ---- debugging ------------------------------------------------------------------------------
     def enable_taps(self, on: bool = True):
         capi.check(self.lib.ds_enable_taps(self.h, int(on)))

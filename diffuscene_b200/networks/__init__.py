@@ -19,8 +19,9 @@ def optimizer_factory(config, parameters):
     weight_decay = 0.0
     if optimizer == "SGD":
         return torch.optim.SGD(parameters, lr=lr, momentum=momentum, weight_decay=weight_decay)
-    if optimizer == "Adam":
-        return torch.optim.Adam(parameters, lr=lr, weight_decay=weight_decay)
+    if optimizer == "Adam":      # a torch.optim.Adam whose step() is one fused kernel on the native training path
+        from ..optim import NativeAdam
+        return NativeAdam(parameters, lr=lr, weight_decay=weight_decay)
     if optimizer == "RAdam":
         return torch.optim.RAdam(parameters, lr=lr, weight_decay=weight_decay)
     raise NotImplementedError()

@@ -24,7 +24,8 @@ import torch.nn as nn
 from torch.nn.utils import clip_grad_norm_
 
 from ..engine import DenoiserEngine
-from ..parallel import allreduce_gradients
+from ..optim import NativeAdam
+from ..parallel import allreduce_flat, allreduce_gradients
 from ..schedule import get_betas, make_tables
 from ..stats_logger import StatsLogger
 from ..weights import NetSpec, seeded_tensor, unet1d_param_specs
@@ -43,6 +44,26 @@ def _register(root: nn.Module, dotted: str, param: nn.Parameter):
             mod.add_module(part, _Tree())
         mod = mod._modules[part]
     mod.register_parameter(parts[-1], param)
+
+
+class _NativeTrainLoss(torch.autograd.Function):
+    """p_losses(...).mean() with the forward AND the backward pass of the denoiser in the CUDA library (ds_train_step).
+    The only differentiable input is the conditioning tensor (its gradient flows on into positional_embedding / the
+    condition MLPs through ordinary autograd); the denoiser parameters receive their gradients as views of the
+    model's flat gradient buffer when backward() runs."""
+
+    @staticmethod
+    def forward(ctx, cond, model, x0, t, noise, shared):
+        losses, ld, dcond = model._native_fwd_bwd(x0, t, noise, cond, shared)
+        ctx.model, ctx.dcond = model, dcond
+        model._last_loss_dict = ld
+        return losses.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.model._assign_native_grads(g)
+        d = ctx.dcond
+        return (None if d is None else d * g), None, None, None, None, None
 
 
 class DiffusionSceneLayout_DDPM(nn.Module):
@@ -152,6 +173,11 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         self._precision = precision
         self._backend = gemm_backend
         self._engine: Optional[DenoiserEngine] = None
+        self._flat = None
+        self._flat_layout = None
+        self._flat_grads = None
+        self._native_grads_ready = False
+        self.native_backward = True      # False: differentiate functional.DenoiserFn with torch autograd instead
         self._weights_version = 0
         self._engine_version = -1
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.mark_weights_dirty())
@@ -174,7 +200,9 @@ class DiffusionSceneLayout_DDPM(nn.Module):
     def _device(self) -> torch.device:
         return next(self.parameters()).device
 
-    def engine(self) -> DenoiserEngine:
+    def engine(self, commit: bool = True) -> DenoiserEngine:
+        """The CUDA engine of this model; commit=False skips the refresh of the sampling-side packed weights (the
+        training step reads the flat parameter buffer directly)."""
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("DiffusionSceneLayout_DDPM runs on a CUDA device only (no CPU fallback); call .to('cuda')")
@@ -182,11 +210,62 @@ class DiffusionSceneLayout_DDPM(nn.Module):
             self._engine = DenoiserEngine(self.spec, self.sample_num_points, self.time_num, precision=self._precision,
                                           gemm_backend=self._backend, device=dev.index or 0)
             self._engine.set_schedule(self.tables)
-        if self._engine_version != self._weights_version:
+        if commit and self._engine_version != self._weights_version:
             sd = {n: p.detach() for n, p in self.named_parameters() if n.startswith("diffusion.model.")}
             self._engine.load_state_dict(sd)
             self._engine_version = self._weights_version
         return self._engine
+
+    # ---- native training: flat parameter / gradient buffers ---------------------------------------
+    def native_training_supported(self) -> bool:
+        return (not self.text_condition) and self.sample_num_points <= 32 and self._device().type == "cuda"
+
+    def _ensure_flat(self):
+        """All denoiser parameters as views into ONE flat fp32 device buffer (ds_expected_weight order), gradients
+        likewise: the native training step, the fused Adam and the data-parallel all-reduce work on these two
+        contiguous buffers; state_dict / load_state_dict / optimizers keep seeing ordinary nn.Parameters."""
+        eng = self.engine(commit=False)
+        params = dict(self.named_parameters())
+        if self._flat is not None:
+            base = self._flat.data_ptr()
+            if all(params[n].data_ptr() == base + 4 * off for n, (off, _) in self._flat_layout.items()):
+                return eng
+        layout = eng.flat_layout()
+        total = sum(n for _, n in layout.values())
+        dev = self._device()
+        flat = torch.empty(total, device=dev, dtype=torch.float32)
+        for name, (off, n) in layout.items():
+            p = params[name]
+            flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            p._ds_flat_owner = self
+        self._flat, self._flat_layout = flat, layout
+        self._flat_grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        self._native_grads_ready = False
+        return eng
+
+    def _native_fwd_bwd(self, x0, t, noise, cond, shared):
+        eng = self._ensure_flat()
+        world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        losses, ld, dcond = eng.train_step(self._flat, x0, t, noise, cond, shared, self.loss_separate, self.loss_iou,
+                                           self.bounds, flat_grads=self._flat_grads, grad_scale=1.0 / world)
+        self._native_grads_ready = False
+        return losses, ld, dcond
+
+    def _assign_native_grads(self, g):
+        """Called from the autograd node of the native loss: expose the flat gradient buffer as the .grad of every
+        denoiser parameter (views, no copies)."""
+        if not (torch.is_tensor(g) and g.numel() == 1 and float(g) == 1.0):
+            self._flat_grads.mul_(g)
+        params = dict(self.named_parameters())
+        for name, (off, n) in self._flat_layout.items():
+            p = params[name]
+            view = self._flat_grads[off:off + n].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() == view.data_ptr():
+                p.grad = view
+            else:                      # gradient accumulation across several backward() calls
+                p.grad = p.grad + view
+        self._native_grads_ready = True
 
     def _denoiser_params(self) -> Dict[str, torch.Tensor]:
         pre = "diffusion.model."
@@ -280,6 +359,13 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         t = torch.randint(0, self.time_num, (B,), device=device) if t is None else t.to(device)
         noise = torch.randn_like(target) if noise is None else noise.to(device)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self.native_backward and self.native_training_supported():
+                c = cond if cond.requires_grad else cond.detach().requires_grad_(True)
+                loss = _NativeTrainLoss.apply(c, self, target, t, noise, shared)
+                ld = self._last_loss_dict
+                if self.room_arrange_condition:
+                    ld = {k: ld[k] for k in ("loss.trans", "loss.angle")}
+                return loss, ld
             losses, ld = self._p_losses_autograd(target, t, noise, cond, shared, cross)
         else:
             losses, ld = self.p_losses_native(target, t, noise, cond, shared, cross)
@@ -476,12 +562,19 @@ class DiffusionSceneLayout_DDPM(nn.Module):
 
 def train_on_batch(model, optimizer, sample_params, config):
     """Reference diffusion_scene_layout_ddpm.py:456-473 (the 11 per-key `.item()` syncs collapse into one)."""
-    optimizer.zero_grad()
+    optimizer.zero_grad(set_to_none=True)
     loss, loss_dict = model.get_loss(sample_params)
     loss.backward()
-    allreduce_gradients(model.parameters())       # no-op outside a torch.distributed process group
-    grad_norm = clip_grad_norm_(model.parameters(), config["training"]["max_grad_norm"])
-    optimizer.step()
+    max_norm = config["training"]["max_grad_norm"]
+    if getattr(model, "_native_grads_ready", False) and isinstance(optimizer, NativeAdam):
+        # native path: gradients live in one flat buffer -> one all-reduce stream, device-side global norm, and the
+        # clip coefficient applied inside the fused Adam kernel (no host synchronisation until the log values below)
+        allreduce_flat(model._flat_grads, [p for p in model.parameters() if p.grad is not None and not hasattr(p, "_ds_flat_owner")])
+        grad_norm = optimizer.step_clipped(model, max_norm)
+    else:
+        allreduce_gradients(model.parameters())       # no-op outside a torch.distributed process group
+        grad_norm = clip_grad_norm_(model.parameters(), max_norm)
+        optimizer.step()
     model.mark_weights_dirty()
     keys = list(loss_dict.keys())
     vals = torch.stack([loss_dict[k].detach().float() for k in keys] + [grad_norm.detach().float(), loss.detach().float()]).tolist()

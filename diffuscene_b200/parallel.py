@@ -83,3 +83,31 @@ def allreduce_gradients(params, bucket_bytes: int = 64 << 20) -> int:
         size += g.numel() * g.element_size()
     flush()
     return n_coll
+
+
+def allreduce_flat(flat_grads: torch.Tensor, other_params=(), bucket_bytes: int = 64 << 20) -> int:
+    """Data-parallel gradient all-reduce of the native training path: the denoiser's gradients already ARE one flat
+    fp32 buffer (diffuscene_b200.engine.DenoiserEngine.flat_layout), so each ~64 MB bucket is a view -- no packing, no
+    copy back.  The native backward pre-scales its gradients by 1 / world_size (ds_train_step grad_scale), so a SUM
+    all-reduce yields the mean.  `other_params`: the few parameters outside the denoiser (positional embedding,
+    condition MLPs), reduced together in one small extra bucket.  Returns the number of collectives issued."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    n_coll = 0
+    step = max(1, bucket_bytes // 4)
+    handles = []
+    for off in range(0, flat_grads.numel(), step):
+        handles.append(dist.all_reduce(flat_grads[off:off + step], op=dist.ReduceOp.SUM, async_op=True))
+        n_coll += 1
+    others = [p.grad for p in other_params if p.grad is not None]
+    if others:
+        buf = torch.cat([g.reshape(-1) for g in others])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)      # already scaled by 1 / world through d(context)
+        off = 0
+        for g in others:
+            g.copy_(buf[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        n_coll += 1
+    for hd in handles:
+        hd.wait()
+    return n_coll

@@ -74,7 +74,9 @@ typedef struct ds_config {
                                3: + epilogue-bound plain GEMMs on that kernel;
                                4: + to_out + LayerNorm + residual of the attention wrappers
                                   as one GEMM with a LayerNorm epilogue                  */
-  int32_t reserved[7];
+  int32_t train;            /* 1: training step program -- one op per reference layer (no fused epilogues, activations
+                               as their own ops), every intermediate kept for the backward pass (ds_train_*)   */
+  int32_t reserved[6];
 } ds_config;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
@@ -172,6 +174,33 @@ DS_API int ds_q_sample(ds_handle* h, const float* x0_dev, const int64_t* t_dev, 
 DS_API int ds_p_losses(ds_handle* h, const float* x0_dev, const int64_t* t_dev, const float* noise_dev,
                 int32_t loss_separate, int32_t loss_iou, const float* bounds_host,
                 float* losses_dev, float* loss_dict_dev, int32_t batch, void* stream);
+
+/* ---- native training step ---------------------------------------------------------------------
+ * Replaces what `loss.backward()` + `optimizer.step()` do in train_on_batch
+ * (scene_synthesis/networks/diffusion_scene_layout_ddpm.py:456-473) for the denoiser: forward of p_losses
+ * (diffusion_ddpm.py:520-652) with every intermediate kept, then the hand-written backward pass of every layer of
+ * Unet1D (denoise_net.py:78-593: weight-standardised convs, GroupNorm + FiLM + SiLU blocks, LayerNorms, linear /
+ * softmax attention, the time-embedding MLP and all FiLM projections) and of the loss (MSE terms + IoU regulariser).
+ * Parameters and gradients are ONE flat fp32 device buffer each, laid out in ds_expected_weight() order
+ * (ds_train_param_count() floats).  grad_scale multiplies d(mean-over-batch loss); pass 1 / world_size to get the
+ * data-parallel mean after a sum all-reduce.  context [ctx_shared ? N : B*N, cond_dim] is the conditioning input of
+ * Unet1D.forward; dcontext_dev (optional, same shape) receives its gradient (it continues into
+ * positional_embedding / the condition MLPs on the caller's side).  flat_grads_dev == NULL: forward + loss only.
+ * Uses the handle's schedule (ds_set_schedule) and precision; networks with text cross-attention are not supported. */
+DS_API int64_t ds_train_param_count(ds_handle* h);
+DS_API int ds_train_step(ds_handle* h, const float* flat_params_dev, const float* x0_dev, const int64_t* t_dev,
+                         const float* noise_dev, const float* context_dev, int32_t ctx_batch, int32_t ctx_shared,
+                         int32_t loss_separate, int32_t loss_iou, const float* bounds_host, float grad_scale,
+                         float* losses_dev, float* loss_dict_dev, float* flat_grads_dev, float* dcontext_dev,
+                         int32_t batch, void* stream);
+/* out[0] += sum(g^2) (device scalar; the caller zeroes it) -- the global gradient norm of clip_grad_norm_. */
+DS_API int ds_sumsq(const float* g_dev, int64_t n, float* out_dev, void* stream);
+/* torch.optim.Adam (weight decay 0, networks/__init__.py:15-34) on flat buffers.  sumsq_dev (optional): device
+ * scalar holding the squared L2 norm of ALL gradients; with max_norm > 0 the clip coefficient
+ * min(1, max_norm / (norm + 1e-6)) of clip_grad_norm_ is applied to the gradient on the fly. */
+DS_API int ds_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n,
+                        float lr, float beta1, float beta2, float eps, int32_t step, const float* sumsq_dev,
+                        float max_norm, void* stream);
 
 /* ---- post-processing: object retrieval -----------------------------------------------------
  * Replaces ThreedFutureDataset.get_closest_furniture_to_objfeats_and_size (mode 0), _to_objfeats (mode 1) and

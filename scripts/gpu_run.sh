@@ -37,6 +37,11 @@ run_task() {
       tail -2 gpurun_out/${TAG}_full.log | cut -c1-300; ls -la gpurun_out/${TAG}_*.ncu-rep ;;
     probe)
       GNT_ONLY=1 timeout 600 python tests/gpu_trace_gemm.py 2>&1 | tee gpurun_out/${TAG}_gemm_probe.txt | grep -v "^   prod_wait" | tail -60 ;;
+    probe-ab)      # A/B of the k_gemm_gnt switches on one box: statistics exchange x residual L2 prefetch
+      for pair in 0 1; do for pf in 0 1; do
+        echo "== DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf"
+        DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -E "^(GNT|T qkv|T to_out|T enc.l1)" | grep "M=49152"
+      done; done | tee gpurun_out/${TAG}_probe_ab.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
