@@ -357,18 +357,31 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
   CK(cudaMemsetAsync(t->dvarena, 0, t->v_total * 4, s));
   CK(cudaMemsetAsync(grads, 0, (size_t)t->flat_n * 4, s));
   CK(cudaMemsetAsync(t->dctx_film, 0, (size_t)ctx_rows * ncb * 2 * C * 4, s));
-  std::map<std::pair<int, int>, bool> seen;      // (buffer, first column) -> its gradient slice has been written
-  seen[{P.out_buf, 0}] = true;
-  auto first_write = [&](int buf, int col) {      // returns the accumulate flag and marks the slice
-    auto key = std::make_pair(buf, col);
-    const bool acc = seen.count(key) > 0;
-    seen[key] = true;
-    return acc ? 1 : 0;
+  // which column ranges of every gradient buffer have been written so far: the first writer overwrites, later ones
+  // accumulate (buffers with several consumers: residual stream, U-Net skips, column-sliced MLP buffers)
+  std::vector<std::vector<std::pair<int, int>>> seen(P.buf_width.size());
+  auto covered = [&](int buf, int col, int width) {      // is [col, col + width) inside the union of the written ranges?
+    int cur = col;
+    bool moved = true;
+    while (cur < col + width && moved) {
+      moved = false;
+      for (auto& iv : seen[buf])
+        if (iv.first <= cur && cur < iv.second) { cur = iv.second; moved = true; break; }
+    }
+    return cur >= col + width;
   };
+  seen[P.out_buf].push_back({0, P.buf_width[P.out_buf]});
+  auto first_write_w = [&](int buf, int col, int width) {      // returns the accumulate flag and marks the range
+    if (covered(buf, col, width)) return 1;
+    seen[buf].push_back({col, col + width});
+    return 0;
+  };
+  auto first_write = [&](int buf, int col) { return first_write_w(buf, col, col == 0 ? P.buf_width[buf] : 0); };
   for (int idx = int(P.ops.size()) - 1; idx >= 0; --idx) {
     const Op& o = P.ops[idx];
     if (o.kind == OP_PACK) continue;
-    if (!seen.count({o.out, o.out_col})) return fail(DS_ERR_STATE, "op '%s': output gradient was never produced", o.name.c_str());
+    if (!covered(o.out, o.out_col, o.N))
+      return fail(DS_ERR_STATE, "op '%s': output gradient was never produced", o.name.c_str());
     switch (o.kind) {
       case OP_GEMM: {
         const T* gD = gptr(o.out, o.out_col);
@@ -383,7 +396,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
           launch_gemm_tn<T, T>(gD, ldg, ptr(in.buf, in.col), ld(in.buf), dW + koff, K, M, o.N, in.k, s);
           if (in.buf != t->pack_buf)
             launch_gemm_nn<T, T, T>(gD, ldg, W + koff, K, gptr(in.buf, in.col), ld(in.buf), M, in.k, o.N,
-                                    first_write(in.buf, in.col), s);
+                                    first_write_w(in.buf, in.col, in.k), s);
           koff += in.k;
         }
         if (o.b >= 0) launch_colsum<T>(gD, ldg, t->dvarena + t->v_off[o.b], M, o.N, s);
@@ -391,7 +404,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         break;
       }
       case OP_ACT:
-        first_write(o.in0.buf, o.in0.col);
+        first_write_w(o.in0.buf, o.in0.col, o.N);
         launch_act_bwd<T>(ptr(o.in0.buf, o.in0.col), ld(o.in0.buf), gptr(o.out, o.out_col), ld(o.out),
                           gptr(o.in0.buf, o.in0.col), ld(o.in0.buf), M, o.N, o.act, s);
         break;
