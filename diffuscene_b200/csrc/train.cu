@@ -93,6 +93,8 @@ struct TrainState {
   int* t_int = nullptr;
   float* x_t = nullptr;
   float* loss_parts = nullptr;
+  cudaEvent_t ev[7] = {nullptr};      // phase boundaries of the last step (ds_train_phase_ms)
+  bool ev_valid = false;
 };
 
 void train_state_destroy(TrainState* t) {
@@ -104,6 +106,7 @@ void train_state_destroy(TrainState* t) {
                    t->ctx_film, t->dctx_film, t->dctx_act, t->x_t, t->loss_parts})
     cudaFree(p);
   cudaFree(t->t_idx); cudaFree(t->t_int);
+  for (auto e : t->ev) if (e) cudaEventDestroy(e);
   delete t;
 }
 
@@ -240,6 +243,9 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
   auto gptr = [&](int buf, int col) -> T* { return buf < 0 ? nullptr : (T*)t->gbufs[buf] + col; };
   auto ld = [&](int buf) { return buf < 0 ? 0 : P.buf_width[buf]; };
 
+  for (auto& e : t->ev) if (!e) cudaEventCreate(&e);
+  t->ev_valid = false;
+  cudaEventRecord(t->ev[0], s);
   // ---- 1. weights: flat fp32 -> packed matrices (weight standardisation folded, storage dtype) and vectors
   for (size_t i = 0; i < P.wmats.size(); ++i) {
     const WRecipe& r = P.wmats[i];
@@ -252,6 +258,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
     for (const VPiece& pc : P.vecs[i].pieces)
       k_vec_add<<<(pc.n + 255) / 256, 256, 0, s>>>(t->varena + t->v_off[i] + pc.off, F(pc.name), pc.n);
 
+  cudaEventRecord(t->ev[1], s);
   // ---- 2. forward
   launch_q_sample(x0, t64, noise, t->x_t, h->sched_dev[S_SQRT_AC], h->sched_dev[S_SQRT_1MAC], B, n_obj * P.d, s);
   launch_t_convert(t64, t->t_int, B, s);
@@ -333,6 +340,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
     h->launches++;
   }
 
+  cudaEventRecord(t->ev[2], s);
   // ---- 3. loss value (per-sample losses + the 9 dict means) and d(loss) / d(model output)
   LossArgs a;
   memset(&a, 0, sizeof a);
@@ -352,6 +360,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
                          h->sched_dev[S_SQRT_RECIP], h->sched_dev[S_SQRT_RECIPM1], h->sched_dev[S_LW], h->sched_dev[S_AC], a,
                          (T*)t->gbufs[P.out_buf], P.dpad, P.dpad, B, grad_scale, s);
 
+  cudaEventRecord(t->ev[3], s);
   // ---- 4. backward through the step program
   CK(cudaMemsetAsync(t->dwarena, 0, t->dw_total * 4, s));
   CK(cudaMemsetAsync(t->dvarena, 0, t->v_total * 4, s));
@@ -444,6 +453,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
     h->launches++;
   }
 
+  cudaEventRecord(t->ev[4], s);
   // ---- 5. conditioning paths (fp32): FiLM projections, time MLP, context
   for (int i = 0; i < ntb; ++i) {
     const float* df = t->dfilm + (size_t)i * 2 * C;
@@ -470,6 +480,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
   if (dcontext)
     k_mul_actgrad<<<((int64_t)ctx_rows * E + 255) / 256, 256, 0, s>>>(t->dctx_act, context, dcontext, (int64_t)ctx_rows * E, ACT_SILU);
 
+  cudaEventRecord(t->ev[5], s);
   // ---- 6. packed gradients -> named tensors (weight-standardisation adjoint on the way)
   for (size_t i = 0; i < P.wmats.size(); ++i) {
     const WRecipe& r = P.wmats[i];
@@ -480,6 +491,8 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
   for (size_t i = 0; i < P.vecs.size(); ++i)
     for (const VPiece& pc : P.vecs[i].pieces)
       CK(cudaMemcpyAsync(G(pc.name), t->dvarena + t->v_off[i] + pc.off, (size_t)pc.n * 4, cudaMemcpyDeviceToDevice, s));
+  cudaEventRecord(t->ev[6], s);
+  t->ev_valid = true;
   CK(cudaGetLastError());
   return 0;
 }
@@ -513,6 +526,13 @@ extern "C" int ds_train_step(ds_handle* h, const float* flat_params_dev, const f
                               loss_iou, bounds_host, grad_scale, losses_dev, loss_dict_dev, flat_grads_dev, dcontext_dev, batch, s);
   return train_step_t<float>(h, flat_params_dev, x0_dev, t_dev, noise_dev, context_dev, ctx_batch, ctx_shared, loss_separate,
                              loss_iou, bounds_host, grad_scale, losses_dev, loss_dict_dev, flat_grads_dev, dcontext_dev, batch, s);
+}
+
+extern "C" int ds_train_phase_ms(ds_handle* h, float* out6) {
+  if (!h || !out6 || !h->train || !h->train->ev_valid) return fail(DS_ERR_STATE, "no completed training step with gradients");
+  CK(cudaEventSynchronize(h->train->ev[6]));
+  for (int i = 0; i < 6; ++i) CK(cudaEventElapsedTime(out6 + i, h->train->ev[i], h->train->ev[i + 1]));
+  return 0;
 }
 
 extern "C" int ds_sumsq(const float* g_dev, int64_t n, float* out_dev, void* stream) {

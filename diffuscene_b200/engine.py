@@ -255,6 +255,11 @@ class DenoiserEngine:
                                           self._stream()))
         return losses, {k: ld[i] for i, k in enumerate(LOSS_KEYS)}, dctx
 
+    def train_phase_ms(self):
+        out = (C.c_float * 6)()
+        capi.check(self.lib.ds_train_phase_ms(self.h, out))
+        return dict(zip(("pack", "forward", "loss", "backward", "cond_paths", "unpack"), [float(v) for v in out]))
+
     # ---- debugging ------------------------------------------------------------------------------
     def enable_taps(self, on: bool = True):
         capi.check(self.lib.ds_enable_taps(self.h, int(on)))

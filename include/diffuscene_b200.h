@@ -193,6 +193,10 @@ DS_API int ds_train_step(ds_handle* h, const float* flat_params_dev, const float
                          int32_t loss_separate, int32_t loss_iou, const float* bounds_host, float grad_scale,
                          float* losses_dev, float* loss_dict_dev, float* flat_grads_dev, float* dcontext_dev,
                          int32_t batch, void* stream);
+/* Device time of the phases of the last ds_train_step with gradients, milliseconds (profiling aid; synchronises):
+ * weight packing, forward, loss + d(loss)/d(output), backward through the step program, conditioning paths,
+ * gradient unpacking (weight-standardisation adjoint). */
+DS_API int ds_train_phase_ms(ds_handle* h, float* out6);
 /* out[0] += sum(g^2) (device scalar; the caller zeroes it) -- the global gradient norm of clip_grad_norm_. */
 DS_API int ds_sumsq(const float* g_dev, int64_t n, float* out_dev, void* stream);
 /* torch.optim.Adam (weight decay 0, networks/__init__.py:15-34) on flat buffers.  sumsq_dev (optional): device
