@@ -696,7 +696,8 @@ void launch_p_losses_bwd(const float* x0, const float* noise, const float* x_t, 
 // ------------------------------------------------------------------------------------------------
 // one warp per row of a piece: dst[row_off + r][col_off + c] = (ws ? standardised : plain) src[r][c]
 template <typename T>
-__global__ void k_pack_piece(const float* __restrict__ src, int rows, int cols, T* __restrict__ dst, int ldd, int ws) {
+__global__ void k_pack_piece(const float* __restrict__ src, int rows, int cols, T* __restrict__ dst, int ldd, int ws,
+                             T* __restrict__ dstT, int ldt) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float* sr = src + (int64_t)r * cols;
@@ -713,11 +714,35 @@ __global__ void k_pack_piece(const float* __restrict__ src, int rows, int cols, 
     fm = float(m);
     rs = 1.0f / sqrtf(float(v) + 1e-5f);
   }
-  for (int c = lane; c < cols; c += 32) stf(dst + (int64_t)r * ldd + c, ws ? (sr[c] - fm) * rs : sr[c]);
+  for (int c = lane; c < cols; c += 32) {
+    const float v = ws ? (sr[c] - fm) * rs : sr[c];
+    stf(dst + (int64_t)r * ldd + c, v);
+    if (dstT) stf(dstT + (int64_t)c * ldt + r, v);      // transposed copy [K, N]: the K-major operand of dX = dY W
+  }
 }
 template <typename T>
-void launch_pack_piece(const float* src, int rows, int cols, T* dst, int ldd, int ws, cudaStream_t s) {
-  if (rows > 0) k_pack_piece<T><<<cdiv64(rows, 8), 256, 0, s>>>(src, rows, cols, dst, ldd, ws);
+void launch_pack_piece(const float* src, int rows, int cols, T* dst, int ldd, int ws, T* dstT, int ldt, cudaStream_t s) {
+  if (rows > 0) k_pack_piece<T><<<cdiv64(rows, 8), 256, 0, s>>>(src, rows, cols, dst, ldd, ws, dstT, ldt);
+}
+// out[c][m] = in[m][c] for m < M, 0 for M <= m < Mcap  (token-major activations -> the K-major operands of dW = dY^T X)
+template <typename T>
+__global__ void k_transpose_pad(const T* __restrict__ in, int ld, T* __restrict__ out, int ldo, int M, int Mcap, int C) {
+  __shared__ float tile[32][33];
+  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int m = m0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (m < M && c < C) ? ldf(in + (int64_t)m * ld + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, m = m0 + threadIdx.x;
+    if (c < C && m < Mcap) stf(out + (int64_t)c * ldo + m, tile[threadIdx.x][i]);
+  }
+}
+template <typename T>
+void launch_transpose_pad(const T* in, int ld, T* out, int ldo, int M, int Mcap, int C, cudaStream_t s) {
+  dim3 grid((Mcap + 31) / 32, (C + 31) / 32), block(32, 8);
+  k_transpose_pad<T><<<grid, block, 0, s>>>(in, ld, out, ldo, M, Mcap, C);
 }
 // gradient of a piece: dsrc[r][c] = (ws adjoint of) dpacked[row_off + r][col_off + c]
 __global__ void k_unpack_piece_grad(const float* __restrict__ dpacked, int ldp, const float* __restrict__ w, int rows,
@@ -816,7 +841,8 @@ void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float 
   template void launch_p_losses_bwd<T>(const float*, const float*, const float*, const T*, int, const int64_t*,       \
                                        const float*, const float*, const float*, const float*, const float*,          \
                                        const float*, LossArgs, T*, int, int, int, float, cudaStream_t);               \
-  template void launch_pack_piece<T>(const float*, int, int, T*, int, int, cudaStream_t);                             \
+  template void launch_pack_piece<T>(const float*, int, int, T*, int, int, T*, int, cudaStream_t);                    \
+  template void launch_transpose_pad<T>(const T*, int, T*, int, int, int, int, cudaStream_t);                         \
   template void launch_gemm_nn<T, T, T>(const T*, int, const T*, int, T*, int, int, int, int, int, cudaStream_t);     \
   template void launch_gemm_tn<T, T>(const T*, int, const T*, int, float*, int, int, int, int, cudaStream_t);
 INSTB(float)

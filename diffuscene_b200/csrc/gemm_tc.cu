@@ -56,6 +56,8 @@ struct TcEpi {
   FilmRef film;
   int film_uniform;      // FILM_TIME only: t[] holds one value for the whole launch (sampling loop)
   int plain;             // channels-on-lanes kernel without GroupNorm: bias, activation, residual only
+  float* d32;            // row-major plain kernel: fp32 output accumulated with atomics (split-K weight-gradient GEMMs)
+  int ksplit;            // ... number of K splits (work units = tiles x ksplit)
   int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
 };
@@ -163,19 +165,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   const int num_m = (epi.M + epi.tile_rows - 1) / epi.tile_rows;
   const int num_n = epi.N / BN;
   const int num_mg = (num_m + int(cs) - 1) / int(cs);          // groups of CS consecutive M tiles
-  const int total = num_mg * num_n;                             // cluster tiles
+  const int ksplit = epi.ksplit > 1 ? epi.ksplit : 1;
+  const int tiles_mn = num_mg * num_n;
+  const int total = tiles_mn * ksplit;                          // work units: (cluster tile, K split)
   const int cluster_id = blockIdx.x / cs, num_clusters = gridDim.x / cs;
   const int kblocks = epi.kb0 + epi.kb1;
+  const int kb_per = (kblocks + ksplit - 1) / ksplit;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       unsigned long long tw = 0, tstart = clock64();
-      for (int tile = cluster_id; tile < total; tile += num_clusters) {
+      for (int unit = cluster_id; unit < total; unit += num_clusters) {
+        const int tile = unit % tiles_mn, kb_lo = (unit / tiles_mn) * kb_per, kb_hi = min(kblocks, kb_lo + kb_per);
         const int n_idx = tile % num_n, m_idx = (tile / num_n) * int(cs) + int(crank);   // N fastest: neighbours share A in L2
         const int m0 = m_idx * epi.tile_rows;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           unsigned long long t0 = epi.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
@@ -205,13 +211,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       int ab = 0;
       uint32_t aphase = 0;
       unsigned long long tw_te = 0, tw_f = 0, tstart = clock64();
-      for (int tile = cluster_id; tile < total; tile += num_clusters) {
+      for (int unit = cluster_id; unit < total; unit += num_clusters) {
+        const int kb_lo = (unit / tiles_mn) * kb_per, kb_hi = min(kblocks, kb_lo + kb_per);
         unsigned long long t0 = epi.trace ? clock64() : 0;
         mbar_wait(tempty_bar(ab), aphase ^ 1u, err_flag, 2);
         if (epi.trace) tw_te += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(ab * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           t0 = epi.trace ? clock64() : 0;
           mbar_wait(full_bar(stage), phase, err_flag, 3);
           if (epi.trace) tw_f += clock64() - t0;
@@ -222,7 +229,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), epi.idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), epi.idesc, ((kb - kb_lo) | k) != 0);
           }
           if (cs == 1) umma_commit(empty_bar(stage));     // smem slot reusable once these MMAs have read it
           else umma_commit_mc(empty_bar(stage), cmask);   // ... in every CTA of the cluster
@@ -293,7 +300,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     };
     unsigned long long tw_tf = 0, tstart = clock64(), ntiles = 0;
     int tile_par = 0;
-    for (int tile = cluster_id; tile < total; tile += num_clusters) {
+    for (int unit = cluster_id; unit < total; unit += num_clusters) {
+      const int tile = unit % tiles_mn;
       const int n_idx = tile % num_n, m_idx = (tile / num_n) * int(cs) + int(crank);   // N fastest: neighbours share A in L2
       const int m0 = m_idx * epi.tile_rows;
       const int m = m0 + row_in_tile;
@@ -368,7 +376,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             rg[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok4[i]) rg[i] = __ldg(reinterpret_cast<const uint4*>(rp4[i] + c * 32));
+            // plain (coherent) load, not __ldg: the backward GEMMs accumulate in place (res == d), every address is
+            // read and later written by the same lane
+            if (ok4[i]) rg[i] = *reinterpret_cast<const uint4*>(rp4[i] + c * 32);
           }
         }
       };
@@ -540,6 +550,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
         uint32_t ra[32], rb[32];
         uint4 rga[4], rgb[4];
         auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
+          if (epi.d32) {      // split-K partial sums: fp32 atomics straight from the accumulator (this lane's row)
+            if (row_ok) {
+              float* op = epi.d32 + (int64_t)m * epi.ldd + nbase + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(op + j, __uint_as_float(r[j]));
+            }
+            return;
+          }
           if (c + 1 < CHUNKS) fetch_res(rnext, c + 1);
           float v[32];
           const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase + c * 32);
@@ -1414,6 +1432,8 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.beta = g.beta;
   p->epi.film = g.film;
   p->epi.plain = plain_t ? 1 : 0;
+  p->epi.d32 = nullptr;
+  p->epi.ksplit = 1;
   {
     // measured (profiles/round2_gnt_ab.txt): the prefetch makes the residual variants 4-5 % SLOWER -- off by default
     static const int pf = getenv("DS_GNT_PREFETCH") ? atoi(getenv("DS_GNT_PREFETCH")) : 0;
@@ -1428,6 +1448,17 @@ void tc_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_plan_set_film(TcGemmPlan* p, const FilmRef& f) { p->epi.film = f; }
 void tc_plan_set_trace(TcGemmPlan* p, unsigned long long* trace) { p->epi.trace = trace; }
 void tc_plan_set_uniform_t(TcGemmPlan* p, int uniform) { p->epi.film_uniform = uniform; }
+// split-K mode of the plain row-major kernel: D (fp32, pitch ldd floats) += A W^T, partial sums added with atomics
+void tc_plan_set_atomic_out(TcGemmPlan* p, float* d32, int ldd, int ksplit) {
+  p->epi.d32 = d32;
+  p->epi.ldd = ldd;
+  p->epi.ksplit = ksplit < 1 ? 1 : ksplit;
+}
+void tc_plan_set_residual(TcGemmPlan* p, const void* res) { p->epi.res = (const bf16*)res; }
+int tc_plan_tiles(const TcGemmPlan* p, int M) {
+  const int num_m = (M + p->epi.tile_rows - 1) / p->epi.tile_rows;
+  return ((num_m + p->cluster - 1) / p->cluster) * (p->epi.N / p->bn);
+}
 
 template <int BN, bool GN>
 static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* flag_dev, cudaStream_t s) {
@@ -1533,7 +1564,7 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
     return epi.n_obj == 21 ? launch_gnt<21, false>(p, epi, fd, s) : launch_gnt<12, false>(p, epi, fd, s);
   }
   const int num_m = (M + epi.tile_rows - 1) / epi.tile_rows;
-  const int total_ct = ((num_m + p->cluster - 1) / p->cluster) * (epi.N / p->bn);
+  const int total_ct = ((num_m + p->cluster - 1) / p->cluster) * (epi.N / p->bn) * (epi.ksplit > 1 ? epi.ksplit : 1);
   if (total_ct == 0) return 0;
   int* flag_dev = nullptr;
   cudaHostGetDevicePointer((void**)&flag_dev, g_err_flag, 0);

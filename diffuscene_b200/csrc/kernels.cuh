@@ -124,6 +124,9 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
 void tc_plan_destroy(TcGemmPlan* p);
 void tc_plan_set_film(TcGemmPlan* p, const FilmRef& f);
 void tc_plan_set_trace(TcGemmPlan* p, unsigned long long* trace);
+void tc_plan_set_atomic_out(TcGemmPlan* p, float* d32, int ldd, int ksplit);      // split-K, fp32 atomics (dW GEMMs)
+int tc_plan_tiles(const TcGemmPlan* p, int M);
+void tc_plan_set_residual(TcGemmPlan* p, const void* res);      // nullptr: plain store; == output: accumulate in place
 void tc_plan_set_uniform_t(TcGemmPlan* p, int uniform);   // all scenes share one timestep (sampling loop)   // [grid][8] cycle counters   // FiLM tables may be (re)allocated after planning
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s);   // returns 0 or cudaError
 bool tc_runtime_available(char* err, int err_len);

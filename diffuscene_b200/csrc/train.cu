@@ -34,7 +34,8 @@ void launch_p_losses_bwd(const float* x0, const float* noise, const float* x_t, 
                          const float* sqrt_ac, const float* sqrt_1mac, const float* sqrt_recip_ac,
                          const float* sqrt_recipm1_ac, const float* loss_weight, const float* alphas_cumprod, LossArgs a,
                          T* dout, int ldd, int dpad, int B, float grad_scale, cudaStream_t s);
-template <typename T> void launch_pack_piece(const float* src, int rows, int cols, T* dst, int ldd, int ws, cudaStream_t s);
+template <typename T> void launch_pack_piece(const float* src, int rows, int cols, T* dst, int ldd, int ws, T* dstT, int ldt, cudaStream_t s);
+template <typename T> void launch_transpose_pad(const T* in, int ld, T* out, int ldo, int M, int Mcap, int C, cudaStream_t s);
 void launch_unpack_piece_grad(const float* dpacked, int ldp, const float* w, int rows, int cols, float* dw, int ws, cudaStream_t s);
 void launch_sumsq(const float* g, int64_t n, float* out, cudaStream_t s);
 void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int step,
@@ -93,6 +94,13 @@ struct TrainState {
   int* t_int = nullptr;
   float* x_t = nullptr;
   float* loss_parts = nullptr;
+  // bf16 mode: tensor-core plans.  Forward GEMMs and dX = dY W (W^T copies `wtarena`, K-major) run the row-major
+  // tcgen05 kernel; dW = dY^T X runs it in split-K mode on transposed copies of dY and X (`trA`, `trB`: [C, rows_cap])
+  bool use_tc = false;
+  char* wtarena = nullptr;
+  std::vector<TcGemmPlan*> tc_fwd;
+  std::vector<TcGemmPlan*> tc_dx[2], tc_dw[2];
+  ds::bf16 *trA = nullptr, *trB = nullptr;
   cudaEvent_t ev[7] = {nullptr};      // phase boundaries of the last step (ds_train_phase_ms)
   bool ev_valid = false;
 };
@@ -107,6 +115,12 @@ void train_state_destroy(TrainState* t) {
     cudaFree(p);
   cudaFree(t->t_idx); cudaFree(t->t_int);
   for (auto e : t->ev) if (e) cudaEventDestroy(e);
+  for (auto* p : t->tc_fwd) if (p) tc_plan_destroy(p);
+  for (int k = 0; k < 2; ++k) {
+    for (auto* p : t->tc_dx[k]) if (p) tc_plan_destroy(p);
+    for (auto* p : t->tc_dw[k]) if (p) tc_plan_destroy(p);
+  }
+  cudaFree(t->wtarena); cudaFree(t->trA); cudaFree(t->trB);
   delete t;
 }
 
@@ -155,6 +169,12 @@ static int train_init(ds_handle* h) {
   t->dw_total = dtot;
   CK(cudaMalloc(&t->warena, total));
   CK(cudaMemset(t->warena, 0, total));
+  t->use_tc = h->use_tc;
+  if (const char* e = getenv("DS_TRAIN_TC")) t->use_tc = t->use_tc && atoi(e) != 0;
+  if (t->use_tc) {
+    CK(cudaMalloc(&t->wtarena, total));
+    CK(cudaMemset(t->wtarena, 0, total));
+  }
   CK(cudaMalloc(&t->dwarena, dtot * 4));
   size_t vt = 0;
   t->v_off.resize(P.vecs.size());
@@ -209,6 +229,75 @@ static int train_capacity(ds_handle* h, int n_scenes, int ctx_rows) {
     CK(cudaMalloc(&t->t_idx, B * 4));
     CK(cudaMalloc(&t->t_int, B * 4));
     k_iota<<<(n_scenes + 255) / 256, 256>>>(t->t_idx, n_scenes);
+    if (t->use_tc) {
+      for (auto* p : t->tc_fwd) if (p) tc_plan_destroy(p);
+      for (int k = 0; k < 2; ++k) {
+        for (auto* p : t->tc_dx[k]) if (p) tc_plan_destroy(p);
+        for (auto* p : t->tc_dw[k]) if (p) tc_plan_destroy(p);
+        t->tc_dx[k].assign(P.ops.size(), nullptr);
+        t->tc_dw[k].assign(P.ops.size(), nullptr);
+      }
+      t->tc_fwd.assign(P.ops.size(), nullptr);
+      cudaFree(t->trA); cudaFree(t->trB);
+      int maxw = 0;
+      for (int w : P.buf_width) maxw = std::max(maxw, w);
+      CK(cudaMalloc(&t->trA, (size_t)maxw * t->rows_cap * 2));
+      CK(cudaMalloc(&t->trB, (size_t)maxw * t->rows_cap * 2));
+      char err[256] = "";
+      auto bp = [&](std::vector<void*>& v, int buf, int col) -> bf16* { return buf < 0 ? nullptr : (bf16*)v[buf] + col; };
+      for (size_t i = 0; i < P.ops.size(); ++i) {
+        const Op& o = P.ops[i];
+        if (o.kind != OP_GEMM) continue;
+        const int K = P.wmats[o.w].K, Npad = P.wmats[o.w].N;
+        GemmArgs g;
+        memset(&g, 0, sizeof g);
+        g.a0 = bp(t->bufs, o.in0.buf, o.in0.col); g.lda0 = P.buf_width[o.in0.buf]; g.k0 = o.in0.k;
+        g.a1 = bp(t->bufs, o.in1.buf, o.in1.col); g.lda1 = o.in1.buf >= 0 ? P.buf_width[o.in1.buf] : 0;
+        g.k1 = o.in1.buf >= 0 ? o.in1.k : 0;
+        g.w = t->warena + t->w_off[o.w]; g.ldw = K;
+        g.bias = o.b >= 0 ? t->varena + t->v_off[o.b] : nullptr;
+        g.d = bp(t->bufs, o.out, o.out_col); g.ldd = P.buf_width[o.out];
+        g.res = bp(t->bufs, o.res, 0); g.ldres = o.res >= 0 ? P.buf_width[o.res] : 0;
+        g.M = t->rows_cap; g.N = o.N; g.act = o.act;
+        t->tc_fwd[i] = tc_plan_create(g, t->rows_cap, err, sizeof err);
+        if (!t->tc_fwd[i]) return fail(DS_ERR_CUDA, "train: tcgen05 plan for '%s' failed: %s", o.name.c_str(), err);
+        const Slice* ins[2] = {&o.in0, &o.in1};
+        int koff = 0;
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const Slice& in = *ins[k2];
+          if (in.buf < 0) continue;
+          // dX = dY W : A = dY [M, N], "weights" = W^T rows [koff, koff + k) of [K, Npad]; accumulates in place
+          if (in.buf != t->pack_buf && in.k % 128 == 0 && o.N % 64 == 0) {
+            memset(&g, 0, sizeof g);
+            g.a0 = bp(t->gbufs, o.out, o.out_col); g.lda0 = P.buf_width[o.out]; g.k0 = o.N;
+            g.w = (bf16*)(t->wtarena + t->w_off[o.w]) + (size_t)koff * Npad; g.ldw = Npad;
+            g.d = bp(t->gbufs, in.buf, in.col); g.ldd = P.buf_width[in.buf];
+            g.res = g.d; g.ldres = g.ldd;      // the launcher clears it for first writers
+            g.M = t->rows_cap; g.N = in.k;
+            t->tc_dx[k2][i] = tc_plan_create(g, t->rows_cap, err, sizeof err);
+            if (!t->tc_dx[k2][i]) return fail(DS_ERR_CUDA, "train: dX plan for '%s' failed: %s", o.name.c_str(), err);
+          }
+          // dW = dY^T X on the transposed copies: A = dY^T [N, rows_cap], "weights" = X^T [k, rows_cap]
+          if (in.k % 128 == 0 && o.N % 128 == 0) {
+            memset(&g, 0, sizeof g);
+            g.a0 = t->trA; g.lda0 = t->rows_cap; g.k0 = t->rows_cap;
+            g.w = t->trB; g.ldw = t->rows_cap;
+            g.d = t->trA; g.ldd = 8;             // placeholder (bf16 output unused in atomic mode)
+            g.M = o.N; g.N = in.k;
+            t->tc_dw[k2][i] = tc_plan_create(g, o.N, err, sizeof err);
+            if (!t->tc_dw[k2][i]) return fail(DS_ERR_CUDA, "train: dW plan for '%s' failed: %s", o.name.c_str(), err);
+            const int tiles = tc_plan_tiles(t->tc_dw[k2][i], o.N);
+            int ksplit = std::max(1, (2 * 148) / std::max(1, tiles));
+            const int kblocks = t->rows_cap / 64;
+            ksplit = std::min(ksplit, kblocks);
+            const int kb_per = (kblocks + ksplit - 1) / ksplit;
+            ksplit = (kblocks + kb_per - 1) / kb_per;      // every split owns at least one k-block (the kernel derives kb_per the same way)
+            tc_plan_set_atomic_out(t->tc_dw[k2][i], t->dwarena + t->dw_off[o.w] + koff, K, ksplit);
+          }
+          koff += in.k;
+        }
+      }
+    }
     t->cap_scenes = n_scenes;
   }
   if (ctx_rows > t->ctx_rows_cap) {
@@ -251,7 +340,8 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
     const WRecipe& r = P.wmats[i];
     for (const WPiece& pc : r.pieces)
       launch_pack_piece<T>(F(pc.name), pc.rows, pc.cols, (T*)(t->warena + t->w_off[i]) + (size_t)pc.row_off * r.K + pc.col_off,
-                           r.K, r.ws ? 1 : 0, s);
+                           r.K, r.ws ? 1 : 0,
+                           t->use_tc ? (T*)(t->wtarena + t->w_off[i]) + (size_t)pc.col_off * r.N + pc.row_off : nullptr, r.N, s);
   }
   CK(cudaMemsetAsync(t->varena, 0, t->v_total * 4, s));
   for (size_t i = 0; i < P.vecs.size(); ++i)
@@ -314,7 +404,12 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         g.d = ptr(o.out, o.out_col); g.ldd = ld(o.out);
         g.res = ptr(o.res, 0); g.ldres = ld(o.res);
         g.M = M; g.N = o.N; g.act = o.act;
-        launch_gemm_simt<T>(g, true, s);
+        if (t->use_tc && t->tc_fwd[&o - &P.ops[0]]) {
+          int e = launch_gemm_tc(t->tc_fwd[&o - &P.ops[0]], M, s);
+          if (e) return fail(DS_ERR_CUDA, "train: tcgen05 GEMM '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)e));
+        } else {
+          launch_gemm_simt<T>(g, true, s);
+        }
         break;
       }
       case OP_ACT:
@@ -402,10 +497,24 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         for (int k2 = 0; k2 < 2; ++k2) {
           const Slice& in = *ins[k2];
           if (in.buf < 0) continue;
-          launch_gemm_tn<T, T>(gD, ldg, ptr(in.buf, in.col), ld(in.buf), dW + koff, K, M, o.N, in.k, s);
-          if (in.buf != t->pack_buf)
-            launch_gemm_nn<T, T, T>(gD, ldg, W + koff, K, gptr(in.buf, in.col), ld(in.buf), M, in.k, o.N,
-                                    first_write_w(in.buf, in.col, in.k), s);
+          if (t->use_tc && t->tc_dw[k2][idx]) {
+            if (k2 == 0 || o.in0.buf < 0) launch_transpose_pad<bf16>((const bf16*)gD, ldg, t->trA, t->rows_cap, M, t->rows_cap, o.N, s);
+            launch_transpose_pad<bf16>((const bf16*)ptr(in.buf, in.col), ld(in.buf), t->trB, t->rows_cap, M, t->rows_cap, in.k, s);
+            int e = launch_gemm_tc(t->tc_dw[k2][idx], o.N, s);
+            if (e) return fail(DS_ERR_CUDA, "train: dW GEMM '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)e));
+          } else {
+            launch_gemm_tn<T, T>(gD, ldg, ptr(in.buf, in.col), ld(in.buf), dW + koff, K, M, o.N, in.k, s);
+          }
+          if (in.buf != t->pack_buf) {
+            const int acc = first_write_w(in.buf, in.col, in.k);
+            if (t->use_tc && t->tc_dx[k2][idx]) {
+              tc_plan_set_residual(t->tc_dx[k2][idx], acc ? (const void*)gptr(in.buf, in.col) : nullptr);
+              int e = launch_gemm_tc(t->tc_dx[k2][idx], M, s);
+              if (e) return fail(DS_ERR_CUDA, "train: dX GEMM '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)e));
+            } else {
+              launch_gemm_nn<T, T, T>(gD, ldg, W + koff, K, gptr(in.buf, in.col), ld(in.buf), M, in.k, o.N, acc, s);
+            }
+          }
           koff += in.k;
         }
         if (o.b >= 0) launch_colsum<T>(gD, ldg, t->dvarena + t->v_off[o.b], M, o.N, s);
