@@ -37,6 +37,10 @@ run_task() {
       tail -2 gpurun_out/${TAG}_full.log | cut -c1-300; ls -la gpurun_out/${TAG}_*.ncu-rep ;;
     probe)
       GNT_ONLY=1 timeout 600 python tests/gpu_trace_gemm.py 2>&1 | tee gpurun_out/${TAG}_gemm_probe.txt | grep -v "^   prod_wait" | tail -60 ;;
+    train-launches)   # per-kernel device time of one training iteration (ncu launch list)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_train_launches.csv \
+        python bench.py --config train --steps 1 --warmup 1 "$@" > gpurun_out/${TAG}_train_launches.log 2>&1
+      python scripts/summarize_launches.py gpurun_out/${TAG}_train_launches.csv | tee gpurun_out/${TAG}_train_kernels.txt ;;
     probe-ab)      # A/B of the k_gemm_gnt switches on one box: statistics exchange x residual L2 prefetch
       for pair in 0 1; do for pf in 0 1; do
         echo "== DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf"
