@@ -725,24 +725,37 @@ void launch_pack_piece(const float* src, int rows, int cols, T* dst, int ldd, in
   if (rows > 0) k_pack_piece<T><<<cdiv64(rows, 8), 256, 0, s>>>(src, rows, cols, dst, ldd, ws, dstT, ldt);
 }
 // out[c][m] = in[m][c] for m < M, 0 for M <= m < Mcap  (token-major activations -> the K-major operands of dW = dY^T X)
+// colsum (optional): colsum[c] += sum_m in[m][c] -- the bias gradient, for free while the tile is in shared memory
 template <typename T>
-__global__ void k_transpose_pad(const T* __restrict__ in, int ld, T* __restrict__ out, int ldo, int M, int Mcap, int C) {
+__global__ void k_transpose_pad(const T* __restrict__ in, int ld, T* __restrict__ out, int ldo, int M, int Mcap, int C,
+                                float* __restrict__ colsum) {
   __shared__ float tile[32][33];
+  __shared__ float part[8][33];
   const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  float cs = 0.f;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int m = m0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (m < M && c < C) ? ldf(in + (int64_t)m * ld + c) : 0.f;
+    const float v = (m < M && c < C) ? ldf(in + (int64_t)m * ld + c) : 0.f;
+    tile[i][threadIdx.x] = v;
+    cs += v;
   }
+  if (colsum) part[threadIdx.y][threadIdx.x] = cs;
   __syncthreads();
+  if (colsum && threadIdx.y == 0 && c0 + threadIdx.x < C && m0 < M) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tsum += part[y][threadIdx.x];
+    atomicAdd(colsum + c0 + threadIdx.x, tsum);
+  }
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i, m = m0 + threadIdx.x;
     if (c < C && m < Mcap) stf(out + (int64_t)c * ldo + m, tile[threadIdx.x][i]);
   }
 }
 template <typename T>
-void launch_transpose_pad(const T* in, int ld, T* out, int ldo, int M, int Mcap, int C, cudaStream_t s) {
+void launch_transpose_pad(const T* in, int ld, T* out, int ldo, int M, int Mcap, int C, float* colsum, cudaStream_t s) {
   dim3 grid((Mcap + 31) / 32, (C + 31) / 32), block(32, 8);
-  k_transpose_pad<T><<<grid, block, 0, s>>>(in, ld, out, ldo, M, Mcap, C);
+  k_transpose_pad<T><<<grid, block, 0, s>>>(in, ld, out, ldo, M, Mcap, C, colsum);
 }
 // gradient of a piece: dsrc[r][c] = (ws adjoint of) dpacked[row_off + r][col_off + c]
 __global__ void k_unpack_piece_grad(const float* __restrict__ dpacked, int ldp, const float* __restrict__ w, int rows,
@@ -842,7 +855,7 @@ void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float 
                                        const float*, const float*, const float*, const float*, const float*,          \
                                        const float*, LossArgs, T*, int, int, int, float, cudaStream_t);               \
   template void launch_pack_piece<T>(const float*, int, int, T*, int, int, T*, int, cudaStream_t);                    \
-  template void launch_transpose_pad<T>(const T*, int, T*, int, int, int, int, cudaStream_t);                         \
+  template void launch_transpose_pad<T>(const T*, int, T*, int, int, int, int, float*, cudaStream_t);                 \
   template void launch_gemm_nn<T, T, T>(const T*, int, const T*, int, T*, int, int, int, int, int, cudaStream_t);     \
   template void launch_gemm_tn<T, T>(const T*, int, const T*, int, float*, int, int, int, int, cudaStream_t);
 INSTB(float)

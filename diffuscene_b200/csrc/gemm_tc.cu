@@ -552,9 +552,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
         auto finish = [&](const uint32_t (&r)[32], int c, const uint4 (&rcur)[4], uint4 (&rnext)[4]) {
           if (epi.d32) {      // split-K partial sums: fp32 atomics straight from the accumulator (this lane's row)
             if (row_ok) {
-              float* op = epi.d32 + (int64_t)m * epi.ldd + nbase + c * 32;
+              float* op = epi.d32 + (int64_t)m * epi.ldd + nbase + c * 32;      // 16-byte aligned (ldd, nbase multiples of 4)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(op + j, __uint_as_float(r[j]));
+              for (int j = 0; j < 32; j += 4)      // vector reduction: 4 floats per L2 atomic transaction
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + j), "f"(__uint_as_float(r[j])),
+                             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                             : "memory");
             }
             return;
           }

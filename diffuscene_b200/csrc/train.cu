@@ -35,7 +35,7 @@ void launch_p_losses_bwd(const float* x0, const float* noise, const float* x_t, 
                          const float* sqrt_recipm1_ac, const float* loss_weight, const float* alphas_cumprod, LossArgs a,
                          T* dout, int ldd, int dpad, int B, float grad_scale, cudaStream_t s);
 template <typename T> void launch_pack_piece(const float* src, int rows, int cols, T* dst, int ldd, int ws, T* dstT, int ldt, cudaStream_t s);
-template <typename T> void launch_transpose_pad(const T* in, int ld, T* out, int ldo, int M, int Mcap, int C, cudaStream_t s);
+template <typename T> void launch_transpose_pad(const T* in, int ld, T* out, int ldo, int M, int Mcap, int C, float* colsum, cudaStream_t s);
 void launch_unpack_piece_grad(const float* dpacked, int ldp, const float* w, int rows, int cols, float* dw, int ws, cudaStream_t s);
 void launch_sumsq(const float* g, int64_t n, float* out, cudaStream_t s);
 void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int step,
@@ -101,6 +101,11 @@ struct TrainState {
   std::vector<TcGemmPlan*> tc_fwd;
   std::vector<TcGemmPlan*> tc_dx[2], tc_dw[2];
   ds::bf16 *trA = nullptr, *trB = nullptr;
+  // gradient buckets for the overlapped data-parallel all-reduce: bucket k = flat range [bounds[k], bounds[k + 1]);
+  // its event is recorded as soon as every parameter gradient inside it is final (the backward pass finalises the
+  // flat buffer from its END towards its start: parameters are laid out in forward order)
+  std::vector<int64_t> bucket_bounds;
+  std::vector<cudaEvent_t> bucket_events;
   cudaEvent_t ev[7] = {nullptr};      // phase boundaries of the last step (ds_train_phase_ms)
   bool ev_valid = false;
 };
@@ -287,7 +292,7 @@ static int train_capacity(ds_handle* h, int n_scenes, int ctx_rows) {
             t->tc_dw[k2][i] = tc_plan_create(g, o.N, err, sizeof err);
             if (!t->tc_dw[k2][i]) return fail(DS_ERR_CUDA, "train: dW plan for '%s' failed: %s", o.name.c_str(), err);
             const int tiles = tc_plan_tiles(t->tc_dw[k2][i], o.N);
-            int ksplit = std::max(1, (2 * 148) / std::max(1, tiles));
+            int ksplit = std::max(1, 148 / std::max(1, tiles));      // one wave of CTAs: fewer partial sums to reduce
             const int kblocks = t->rows_cap / 64;
             ksplit = std::min(ksplit, kblocks);
             const int kb_per = (kblocks + ksplit - 1) / ksplit;
@@ -481,6 +486,65 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
     return 0;
   };
   auto first_write = [&](int buf, int col) { return first_write_w(buf, col, col == 0 ? P.buf_width[buf] : 0); };
+  // finalisation bookkeeping (host side, at enqueue time): which named gradients are complete in stream order
+  std::map<std::string, bool> pending;
+  for (auto& kv : t->flat_off) pending[kv.first] = true;
+  std::vector<char> bucket_done(t->bucket_events.size(), 0);
+  auto advance_buckets = [&]() {      // a bucket is final once no pending gradient intersects its flat range
+    for (size_t k = 0; k < t->bucket_events.size(); ++k) {
+      if (bucket_done[k]) continue;
+      const int64_t lo = t->bucket_bounds[k], hi = t->bucket_bounds[k + 1];
+      bool final_ = true;
+      for (auto& kv : pending) {
+        if (!kv.second) continue;
+        const int64_t a0 = t->flat_off.at(kv.first), a1 = a0 + h->plan.expected.at(kv.first);
+        if (a0 < hi && a1 > lo) { final_ = false; break; }
+      }
+      if (final_) {
+        cudaEventRecord(t->bucket_events[k], s);
+        bucket_done[k] = 1;
+      }
+    }
+  };
+  auto unpack_wmat = [&](int w) {
+    const WRecipe& r = P.wmats[w];
+    for (const WPiece& pc : r.pieces) {
+      launch_unpack_piece_grad(t->dwarena + t->dw_off[w] + (size_t)pc.row_off * r.K + pc.col_off, r.K, F(pc.name), pc.rows,
+                               pc.cols, G(pc.name), r.ws ? 1 : 0, s);
+      pending[pc.name] = false;
+    }
+  };
+  auto unpack_vec = [&](int v) -> int {
+    if (v < 0) return 0;
+    for (const VPiece& pc : P.vecs[v].pieces) {
+      CK(cudaMemcpyAsync(G(pc.name), t->dvarena + t->v_off[v] + pc.off, (size_t)pc.n * 4, cudaMemcpyDeviceToDevice, s));
+      pending[pc.name] = false;
+    }
+    return 0;
+  };
+  bool dst_started = false, dctx_started = false;
+  auto time_block_bwd = [&](int i) {      // FiLM projection of time block i: dW, db, and its share of d(SiLU(temb))
+    const float* df = t->dfilm + (size_t)i * 2 * C;
+    launch_gemm_tn<float, float>(df, ntb * 2 * C, t->st, 4 * C, G(P.time_blocks[i] + ".mlp.1.weight"), 4 * C, B, 2 * C, 4 * C, s);
+    launch_colsum<float>(df, ntb * 2 * C, G(P.time_blocks[i] + ".mlp.1.bias"), B, 2 * C, s);
+    launch_gemm_nn<float, float, float>(df, ntb * 2 * C, F(P.time_blocks[i] + ".mlp.1.weight"), 4 * C, t->dst, 4 * C, B, 4 * C,
+                                        2 * C, dst_started ? 1 : 0, s);
+    dst_started = true;
+    pending[P.time_blocks[i] + ".mlp.1.weight"] = false;
+    pending[P.time_blocks[i] + ".mlp.1.bias"] = false;
+  };
+  auto ctx_block_bwd = [&](int i) {
+    const float* df = t->dctx_film + (size_t)i * 2 * C;
+    launch_gemm_tn<float, float>(df, ncb * 2 * C, t->ctx_act, E, G(P.ctx_blocks[i] + ".mlp.1.weight"), E, ctx_rows, 2 * C, E, s);
+    launch_colsum<float>(df, ncb * 2 * C, G(P.ctx_blocks[i] + ".mlp.1.bias"), ctx_rows, 2 * C, s);
+    if (dcontext) {
+      launch_gemm_nn<float, float, float>(df, ncb * 2 * C, F(P.ctx_blocks[i] + ".mlp.1.weight"), E, t->dctx_act, E, ctx_rows, E,
+                                          2 * C, dctx_started ? 1 : 0, s);
+      dctx_started = true;
+    }
+    pending[P.ctx_blocks[i] + ".mlp.1.weight"] = false;
+    pending[P.ctx_blocks[i] + ".mlp.1.bias"] = false;
+  };
   for (int idx = int(P.ops.size()) - 1; idx >= 0; --idx) {
     const Op& o = P.ops[idx];
     if (o.kind == OP_PACK) continue;
@@ -494,12 +558,18 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         float* dW = t->dwarena + t->dw_off[o.w];
         const Slice* ins[2] = {&o.in0, &o.in1};
         int koff = 0;
+        bool bias_done = false, tra_ready = false;
         for (int k2 = 0; k2 < 2; ++k2) {
           const Slice& in = *ins[k2];
           if (in.buf < 0) continue;
           if (t->use_tc && t->tc_dw[k2][idx]) {
-            if (k2 == 0 || o.in0.buf < 0) launch_transpose_pad<bf16>((const bf16*)gD, ldg, t->trA, t->rows_cap, M, t->rows_cap, o.N, s);
-            launch_transpose_pad<bf16>((const bf16*)ptr(in.buf, in.col), ld(in.buf), t->trB, t->rows_cap, M, t->rows_cap, in.k, s);
+            if (!tra_ready) {      // dY^T once per op; its column sums are the bias gradient
+              tra_ready = true;
+              launch_transpose_pad<bf16>((const bf16*)gD, ldg, t->trA, t->rows_cap, M, t->rows_cap, o.N,
+                                         o.b >= 0 ? t->dvarena + t->v_off[o.b] : nullptr, s);
+              bias_done = o.b >= 0;
+            }
+            launch_transpose_pad<bf16>((const bf16*)ptr(in.buf, in.col), ld(in.buf), t->trB, t->rows_cap, M, t->rows_cap, in.k, nullptr, s);
             int e = launch_gemm_tc(t->tc_dw[k2][idx], o.N, s);
             if (e) return fail(DS_ERR_CUDA, "train: dW GEMM '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)e));
           } else {
@@ -517,8 +587,10 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
           }
           koff += in.k;
         }
-        if (o.b >= 0) launch_colsum<T>(gD, ldg, t->dvarena + t->v_off[o.b], M, o.N, s);
+        if (o.b >= 0 && !bias_done) launch_colsum<T>(gD, ldg, t->dvarena + t->v_off[o.b], M, o.N, s);
         if (o.res >= 0) launch_add_block<T>(gD, ldg, gptr(o.res, 0), ld(o.res), M, o.N, first_write(o.res, 0), s);
+        unpack_wmat(o.w);
+        if (unpack_vec(o.b)) return DS_ERR_CUDA;
         break;
       }
       case OP_ACT:
@@ -537,6 +609,9 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         launch_gn_bwd<T>(ptr(o.in0.buf, 0), ld(o.in0.buf), gptr(o.out, 0), ld(o.out), gptr(o.in0.buf, 0), ld(o.in0.buf),
                          gptr(o.res, 0), ld(o.res), racc, t->varena + t->v_off[o.gamma], t->varena + t->v_off[o.beta], f,
                          t->dvarena + t->v_off[o.gamma], t->dvarena + t->v_off[o.beta], dfilm, dstride, B, n_obj, C, 8, s);
+        if (unpack_vec(o.gamma) || unpack_vec(o.beta)) return DS_ERR_CUDA;
+        if (o.film == 1) time_block_bwd(o.film_blk);
+        else if (o.film == 2) ctx_block_bwd(o.film_blk);
         break;
       }
       case OP_LN: {
@@ -544,6 +619,7 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         const int racc = o.res >= 0 ? first_write(o.res, 0) : 0;
         launch_ln_bwd<T>(ptr(o.in0.buf, 0), ld(o.in0.buf), gptr(o.out, 0), ld(o.out), gptr(o.in0.buf, 0), ld(o.in0.buf), xacc,
                          gptr(o.res, 0), ld(o.res), racc, t->varena + t->v_off[o.b], t->dvarena + t->v_off[o.b], M, C, s);
+        if (unpack_vec(o.b)) return DS_ERR_CUDA;
         break;
       }
       case OP_LINATTN:
@@ -560,17 +636,11 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         return fail(DS_ERR_STATE, "op kind %d has no backward", o.kind);
     }
     h->launches++;
+    advance_buckets();
   }
 
   cudaEventRecord(t->ev[4], s);
-  // ---- 5. conditioning paths (fp32): FiLM projections, time MLP, context
-  for (int i = 0; i < ntb; ++i) {
-    const float* df = t->dfilm + (size_t)i * 2 * C;
-    launch_gemm_tn<float, float>(df, ntb * 2 * C, t->st, 4 * C, G(P.time_blocks[i] + ".mlp.1.weight"), 4 * C, B, 2 * C, 4 * C, s);
-    launch_colsum<float>(df, ntb * 2 * C, G(P.time_blocks[i] + ".mlp.1.bias"), B, 2 * C, s);
-    launch_gemm_nn<float, float, float>(df, ntb * 2 * C, F(P.time_blocks[i] + ".mlp.1.weight"), 4 * C, t->dst, 4 * C, B, 4 * C,
-                                        2 * C, i > 0, s);
-  }
+  // ---- 5. what is left of the conditioning paths (fp32): the shared time MLP, d(context)
   k_mul_actgrad<<<((int64_t)B * 4 * C + 255) / 256, 256, 0, s>>>(t->dst, t->temb, t->dtemb, (int64_t)B * 4 * C, ACT_SILU);
   launch_gemm_tn<float, float>(t->dtemb, 4 * C, t->h1, 4 * C, G("time_mlp.3.weight"), 4 * C, B, 4 * C, 4 * C, s);
   launch_colsum<float>(t->dtemb, 4 * C, G("time_mlp.3.bias"), B, 4 * C, s);
@@ -578,28 +648,14 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
   k_mul_actgrad<<<((int64_t)B * 4 * C + 255) / 256, 256, 0, s>>>(t->dh1, t->z1, t->dst, (int64_t)B * 4 * C, ACT_GELU);      // dst := dz1
   launch_gemm_tn<float, float>(t->dst, 4 * C, t->emb, C, G("time_mlp.1.weight"), C, B, 4 * C, C, s);
   launch_colsum<float>(t->dst, 4 * C, G("time_mlp.1.bias"), B, 4 * C, s);
-  for (int i = 0; i < ncb; ++i) {
-    const float* df = t->dctx_film + (size_t)i * 2 * C;
-    launch_gemm_tn<float, float>(df, ncb * 2 * C, t->ctx_act, E, G(P.ctx_blocks[i] + ".mlp.1.weight"), E, ctx_rows, 2 * C, E, s);
-    launch_colsum<float>(df, ncb * 2 * C, G(P.ctx_blocks[i] + ".mlp.1.bias"), ctx_rows, 2 * C, s);
-    if (dcontext)
-      launch_gemm_nn<float, float, float>(df, ncb * 2 * C, F(P.ctx_blocks[i] + ".mlp.1.weight"), E, t->dctx_act, E, ctx_rows, E,
-                                          2 * C, i > 0, s);
-  }
+  for (const char* n : {"time_mlp.1.weight", "time_mlp.1.bias", "time_mlp.3.weight", "time_mlp.3.bias"}) pending[n] = false;
   if (dcontext)
     k_mul_actgrad<<<((int64_t)ctx_rows * E + 255) / 256, 256, 0, s>>>(t->dctx_act, context, dcontext, (int64_t)ctx_rows * E, ACT_SILU);
-
   cudaEventRecord(t->ev[5], s);
-  // ---- 6. packed gradients -> named tensors (weight-standardisation adjoint on the way)
-  for (size_t i = 0; i < P.wmats.size(); ++i) {
-    const WRecipe& r = P.wmats[i];
-    for (const WPiece& pc : r.pieces)
-      launch_unpack_piece_grad(t->dwarena + t->dw_off[i] + (size_t)pc.row_off * r.K + pc.col_off, r.K, F(pc.name), pc.rows,
-                               pc.cols, G(pc.name), r.ws ? 1 : 0, s);
-  }
-  for (size_t i = 0; i < P.vecs.size(); ++i)
-    for (const VPiece& pc : P.vecs[i].pieces)
-      CK(cudaMemcpyAsync(G(pc.name), t->dvarena + t->v_off[i] + pc.off, (size_t)pc.n * 4, cudaMemcpyDeviceToDevice, s));
+  // ---- 6. every named gradient is final: release the remaining buckets
+  for (auto& kv : pending)
+    if (kv.second) return fail(DS_ERR_STATE, "gradient of '%s' was never produced", kv.first.c_str());
+  advance_buckets();
   cudaEventRecord(t->ev[6], s);
   t->ev_valid = true;
   CK(cudaGetLastError());
@@ -635,6 +691,20 @@ extern "C" int ds_train_step(ds_handle* h, const float* flat_params_dev, const f
                               loss_iou, bounds_host, grad_scale, losses_dev, loss_dict_dev, flat_grads_dev, dcontext_dev, batch, s);
   return train_step_t<float>(h, flat_params_dev, x0_dev, t_dev, noise_dev, context_dev, ctx_batch, ctx_shared, loss_separate,
                              loss_iou, bounds_host, grad_scale, losses_dev, loss_dict_dev, flat_grads_dev, dcontext_dev, batch, s);
+}
+
+extern "C" int ds_train_set_buckets(ds_handle* h, const int64_t* bounds, int32_t n_buckets, void* const* events) {
+  if (!h || n_buckets < 0 || (n_buckets > 0 && (!bounds || !events))) return fail(DS_ERR_INVALID, "bad argument to ds_train_set_buckets");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = train_init(h);
+  if (rc) return rc;
+  TrainState* t = h->train;
+  t->bucket_bounds.assign(bounds, bounds + (n_buckets > 0 ? n_buckets + 1 : 0));
+  t->bucket_events.clear();
+  for (int i = 0; i < n_buckets; ++i) t->bucket_events.push_back((cudaEvent_t)events[i]);
+  if (n_buckets > 0 && (t->bucket_bounds.front() != 0 || t->bucket_bounds.back() != t->flat_n))
+    return fail(DS_ERR_INVALID, "bucket bounds must run from 0 to ds_train_param_count()");
+  return 0;
 }
 
 extern "C" int ds_train_phase_ms(ds_handle* h, float* out6) {

@@ -255,6 +255,15 @@ class DenoiserEngine:
                                           self._stream()))
         return losses, {k: ld[i] for i, k in enumerate(LOSS_KEYS)}, dctx
 
+    def train_set_buckets(self, bounds: Sequence[int], events: Sequence["torch.cuda.Event"]):
+        """Gradient buckets for the overlapped all-reduce (see ds_train_set_buckets); `events` are torch.cuda.Event
+        objects (recorded once so that their cudaEvent_t exists), kept alive by this object."""
+        n = len(events)
+        self._bucket_events = list(events)
+        arr_b = (C.c_int64 * (n + 1))(*[int(b) for b in bounds]) if n else None
+        arr_e = (C.c_void_p * n)(*[C.c_void_p(e.cuda_event) for e in events]) if n else None
+        capi.check(self.lib.ds_train_set_buckets(self.h, arr_b, n, arr_e))
+
     def train_phase_ms(self):
         out = (C.c_float * 6)()
         capi.check(self.lib.ds_train_phase_ms(self.h, out))

@@ -177,6 +177,7 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         self._flat_layout = None
         self._flat_grads = None
         self._native_grads_ready = False
+        self._overlap = None
         self.native_backward = True      # False: differentiate functional.DenoiserFn with torch autograd instead
         self._weights_version = 0
         self._engine_version = -1
@@ -242,19 +243,29 @@ class DiffusionSceneLayout_DDPM(nn.Module):
         self._flat, self._flat_layout = flat, layout
         self._flat_grads = torch.zeros(total, device=dev, dtype=torch.float32)
         self._native_grads_ready = False
+        self._overlap = None
         return eng
 
     def _native_fwd_bwd(self, x0, t, noise, cond, shared):
         eng = self._ensure_flat()
         world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        if world > 1 and self._overlap is None:
+            from ..parallel import GradOverlap
+            self._overlap = GradOverlap(eng, self._flat_grads)
         losses, ld, dcond = eng.train_step(self._flat, x0, t, noise, cond, shared, self.loss_separate, self.loss_iou,
                                            self.bounds, flat_grads=self._flat_grads, grad_scale=1.0 / world)
+        if world > 1:
+            # the kernels of the backward pass are only ENQUEUED at this point: the bucket all-reduces go to a side
+            # stream, each gated by the event the engine records when that bucket's gradients are final
+            self._overlap.launch()
         self._native_grads_ready = False
         return losses, ld, dcond
 
     def _assign_native_grads(self, g):
         """Called from the autograd node of the native loss: expose the flat gradient buffer as the .grad of every
         denoiser parameter (views, no copies)."""
+        if self._overlap is not None:
+            self._overlap.wait()                 # the current stream waits for the bucket all-reduces
         if not (torch.is_tensor(g) and g.numel() == 1 and float(g) == 1.0):
             self._flat_grads.mul_(g)
         params = dict(self.named_parameters())
@@ -569,7 +580,9 @@ def train_on_batch(model, optimizer, sample_params, config):
     if getattr(model, "_native_grads_ready", False) and isinstance(optimizer, NativeAdam):
         # native path: gradients live in one flat buffer -> one all-reduce stream, device-side global norm, and the
         # clip coefficient applied inside the fused Adam kernel (no host synchronisation until the log values below)
-        allreduce_flat(model._flat_grads, [p for p in model.parameters() if p.grad is not None and not hasattr(p, "_ds_flat_owner")])
+        # (the flat buffer itself was all-reduced bucket by bucket DURING the backward pass: parallel.GradOverlap)
+        allreduce_flat(None if model._overlap is not None else model._flat_grads,
+                       [p for p in model.parameters() if p.grad is not None and not hasattr(p, "_ds_flat_owner")])
         grad_norm = optimizer.step_clipped(model, max_norm)
     else:
         allreduce_gradients(model.parameters())       # no-op outside a torch.distributed process group

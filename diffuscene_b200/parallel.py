@@ -96,7 +96,7 @@ def allreduce_flat(flat_grads: torch.Tensor, other_params=(), bucket_bytes: int 
     n_coll = 0
     step = max(1, bucket_bytes // 4)
     handles = []
-    for off in range(0, flat_grads.numel(), step):
+    for off in range(0, flat_grads.numel() if flat_grads is not None else 0, step):
         handles.append(dist.all_reduce(flat_grads[off:off + step], op=dist.ReduceOp.SUM, async_op=True))
         n_coll += 1
     others = [p.grad for p in other_params if p.grad is not None]
@@ -111,3 +111,39 @@ def allreduce_flat(flat_grads: torch.Tensor, other_params=(), bucket_bytes: int 
     for hd in handles:
         hd.wait()
     return n_coll
+
+
+class GradOverlap:
+    """Bucketed gradient all-reduce overlapped with the native backward pass.
+
+    The flat gradient buffer is cut into ~64 MB buckets.  ds_train_step records one CUDA event per bucket as soon as
+    every gradient in it is final (the backward pass finalises the buffer from its end towards its start).  launch()
+    is called right after ds_train_step returned -- its kernels are enqueued, not finished -- and enqueues, on a side
+    stream, `wait(event_k)` + all-reduce(bucket k) for every bucket, last bucket first, so NCCL works on the finished
+    tail of the buffer while the GPU still computes the gradients of the earlier layers.  wait() makes the current
+    stream wait for all of them (called before the gradients are consumed)."""
+
+    def __init__(self, engine, flat_grads: torch.Tensor, bucket_bytes: int = 64 << 20):
+        self.flat = flat_grads
+        n = flat_grads.numel()
+        step = max(1, bucket_bytes // 4)
+        self.bounds = list(range(0, n, step)) + [n]
+        self.events = [torch.cuda.Event() for _ in range(len(self.bounds) - 1)]
+        for e in self.events:
+            e.record()                               # materialise the cudaEvent_t handles
+        engine.train_set_buckets(self.bounds, self.events)
+        self.stream = torch.cuda.Stream(device=flat_grads.device)
+        self.works = []
+
+    def launch(self):
+        self.works = []
+        with torch.cuda.stream(self.stream):
+            for k in reversed(range(len(self.events))):
+                self.stream.wait_event(self.events[k])
+                self.works.append(dist.all_reduce(self.flat[self.bounds[k]:self.bounds[k + 1]], op=dist.ReduceOp.SUM, async_op=True))
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)

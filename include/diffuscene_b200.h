@@ -193,6 +193,12 @@ DS_API int ds_train_step(ds_handle* h, const float* flat_params_dev, const float
                          int32_t loss_separate, int32_t loss_iou, const float* bounds_host, float grad_scale,
                          float* losses_dev, float* loss_dict_dev, float* flat_grads_dev, float* dcontext_dev,
                          int32_t batch, void* stream);
+/* Overlap of the data-parallel gradient all-reduce with the backward pass: bucket k is the flat range
+ * [bounds[k], bounds[k + 1]) (bounds[0] = 0, bounds[n] = ds_train_param_count()); ds_train_step records events[k] (a
+ * cudaEvent_t owned by the caller) on its stream as soon as every gradient inside the bucket is final -- the backward
+ * pass finalises the buffer from its end towards its start -- so the caller's communication stream can wait on the
+ * event and all-reduce that bucket while the rest of the backward pass still runs.  n_buckets = 0 clears. */
+DS_API int ds_train_set_buckets(ds_handle* h, const int64_t* bounds, int32_t n_buckets, void* const* events);
 /* Device time of the phases of the last ds_train_step with gradients, milliseconds (profiling aid; synchronises):
  * weight packing, forward, loss + d(loss)/d(output), backward through the step program, conditioning paths,
  * gradient unpacking (weight-standardisation adjoint). */

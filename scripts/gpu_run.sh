@@ -41,6 +41,13 @@ run_task() {
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_train_launches.csv \
         python bench.py --config train --steps 1 --warmup 1 "$@" > gpurun_out/${TAG}_train_launches.log 2>&1
       python scripts/summarize_launches.py gpurun_out/${TAG}_train_launches.csv | tee gpurun_out/${TAG}_train_kernels.txt ;;
+    dp2)              # needs gpurun --gpus 2: data-parallel training check + 2-GPU bench lines
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/gpu_dp_train_check.py 2>&1 | tail -8 | tee gpurun_out/${TAG}_dp2_check.log
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --gpus 2 --config train --steps 5 --warmup 3 2>gpurun_out/${TAG}_dp2_train.err | tail -1 | tee gpurun_out/${TAG}_dp2_train.json
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
+        bench.py --gpus 2 --steps 2 --warmup 2 --no-cpu-baseline "$@" 2>gpurun_out/${TAG}_dp2_sample.err | tail -1 | tee gpurun_out/${TAG}_dp2_sample.json ;;
     probe-ab)      # A/B of the k_gemm_gnt switches on one box: statistics exchange x residual L2 prefetch
       for pair in 0 1; do for pf in 0 1; do
         echo "== DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf"
