@@ -63,6 +63,13 @@ static int run_op(ds_handle* h, int idx, int n_scenes, cudaStream_t s) {
   switch (o.kind) {
     case OP_PACK:
       return DS_ERR_STATE;   // handled by the caller (needs the x pointer)
+    case OP_LN_QKV_ATTN: {
+      if (!h->use_tc || !h->atp[idx]) return fail(DS_ERR_STATE, "fused attention op without the tcgen05 backend");
+      int e = launch_ln_qkv_attn(h->atp[idx], M, s);
+      if (e) return fail(DS_ERR_CUDA, "fused LayerNorm + to_qkv + attention launch '%s' failed: %s", o.name.c_str(),
+                         cudaGetErrorString((cudaError_t)e));
+      break;
+    }
     case OP_GEMM_LN: {
       if (!h->use_tc || !h->lnp[idx]) return fail(DS_ERR_STATE, "fused LayerNorm op without the tcgen05 backend");
       int e = launch_gemm_ln(h->lnp[idx], M, s);
@@ -149,6 +156,8 @@ static void free_buffers(ds_handle* h) {
   h->tc.clear();
   for (auto* p : h->lnp) if (p) ln_plan_destroy(p);
   h->lnp.clear();
+  for (auto* p : h->atp) if (p) attn_qkv_plan_destroy(p);
+  h->atp.clear();
   cudaFree(h->t_dev); h->t_dev = nullptr;
   cudaFree(h->x_state); h->x_state = nullptr;
   cudaFree(h->x_tmp); h->x_tmp = nullptr;
@@ -194,9 +203,18 @@ static int ensure_capacity(ds_handle* h, int n_scenes) {
   CK(cudaMalloc(&h->loss_parts, sizeof(float) * 9 * n_scenes));
   h->tc.assign(P.ops.size(), nullptr);
   h->lnp.assign(P.ops.size(), nullptr);
+  h->atp.assign(P.ops.size(), nullptr);
   if (h->use_tc) {
     for (size_t i = 0; i < P.ops.size(); ++i) {
       const Op& o = P.ops[i];
+      if (o.kind == OP_LN_QKV_ATTN) {
+        char err[256] = "";
+        h->atp[i] = attn_qkv_plan_create((bf16*)h->bufs[o.in0.buf] + o.in0.col, P.buf_width[o.in0.buf], h->warena + h->w_off[o.w],
+                                         P.wmats[o.w].K, h->attn_cs + (size_t)o.w * 384, (bf16*)h->bufs[o.out], P.buf_width[o.out],
+                                         n_obj, P.wmats[o.w].K, h->rows_cap, err, sizeof err);
+        if (!h->atp[i]) return fail(DS_ERR_CUDA, "fused attention plan for op '%s' failed: %s", o.name.c_str(), err);
+        continue;
+      }
       if (o.kind != OP_GEMM && o.kind != OP_GEMM_GN && o.kind != OP_GEMM_LN) continue;
       auto ptr = [&](int buf, int col) -> bf16* { return buf < 0 ? nullptr : (bf16*)h->bufs[buf] + col; };
       GemmArgs g;
@@ -325,10 +343,11 @@ extern "C" int ds_commit_weights(ds_handle* h) {
   }
   std::vector<char> host(total, 0);
   std::vector<float> mat;
+  std::vector<float> attn_cs_host(P.wmats.size() * 384, 0.f);
   std::vector<char> gnt_w(P.wmats.size(), 0);       // weight matrices consumed by fused GroupNorm ops
   std::vector<char> row_major_w(P.wmats.size(), 0);
   for (const Op& o : P.ops) {
-    if (o.kind == OP_GEMM_LN) { row_major_w[o.w] = 1; continue; }
+    if (o.kind == OP_GEMM_LN || o.kind == OP_LN_QKV_ATTN) { row_major_w[o.w] = 1; continue; }
     if (o.kind != OP_GEMM && o.kind != OP_GEMM_GN) continue;
     if (gemm_variant(h, o) >= 2) gnt_w[o.w] = 1;
     else row_major_w[o.w] = 1;
@@ -359,6 +378,27 @@ extern "C" int ds_commit_weights(ds_handle* h) {
         }
       }
     }
+    if (!r.scale_k.empty()) {      // a LayerNorm gain folded into the columns of the following conv (k_ln_qkv_attn)
+      const std::vector<float>* gk = find_w(h, r.scale_k, r.K, &rc);
+      if (!gk) return rc;
+      for (int rr = 0; rr < r.N; ++rr)
+        for (int c = 0; c < r.K; ++c) mat[(size_t)rr * r.K + c] *= (*gk)[c];
+      if (r.N <= 384 && h->bf16_mode) {
+        // column sums of the ROUNDED weights: the kernel subtracts mean * cs from an accumulator built from them
+        std::vector<uint16_t> tmp(mat.size());
+        to_bf16_host(mat.data(), tmp.data(), mat.size());
+        for (int rr = 0; rr < r.N; ++rr) {
+          double acc = 0;
+          for (int c = 0; c < r.K; ++c) {
+            uint32_t u = uint32_t(tmp[(size_t)rr * r.K + c]) << 16;
+            float f;
+            memcpy(&f, &u, 4);
+            acc += f;
+          }
+          attn_cs_host[i * 384 + rr] = float(acc);
+        }
+      }
+    }
     if (gnt_w[i]) {      // row order the channels-on-lanes kernel expects (see tc_gnt_row)
       std::vector<float> pm(mat.size());
       for (int rr = 0; rr < r.N; ++rr) memcpy(pm.data() + (size_t)rr * r.K, mat.data() + (size_t)tc_gnt_row(rr) * r.K, sizeof(float) * r.K);
@@ -371,6 +411,7 @@ extern "C" int ds_commit_weights(ds_handle* h) {
   h->warena = nullptr;
   CK(cudaMalloc(&h->warena, total));
   CK(cudaMemcpy(h->warena, host.data(), total, cudaMemcpyHostToDevice));
+  if ((rc = upload_f32(&h->attn_cs, attn_cs_host.data(), attn_cs_host.size()))) return rc;
   // ---- fp32 vectors ----
   size_t vt = 0;
   h->v_off.resize(P.vecs.size());
@@ -503,7 +544,7 @@ extern "C" int ds_destroy(ds_handle* h) {
   if (h->train) train_state_destroy(h->train);
   h->train = nullptr;
   free_buffers(h);
-  cudaFree(h->warena); cudaFree(h->varena);
+  cudaFree(h->warena); cudaFree(h->varena); cudaFree(h->attn_cs);
   cudaFree(h->time_w1); cudaFree(h->time_b1); cudaFree(h->time_w3); cudaFree(h->time_b3);
   cudaFree(h->time_wall); cudaFree(h->time_ball); cudaFree(h->time_table); cudaFree(h->sin_freq);
   cudaFree(h->ctx_wall); cudaFree(h->ctx_ball); cudaFree(h->ctx_table);

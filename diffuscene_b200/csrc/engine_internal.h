@@ -64,6 +64,8 @@ struct ds_handle {
   std::vector<void*> bufs;
   std::vector<TcGemmPlan*> tc;
   std::vector<LnGemmPlan*> lnp;      // fused GEMM + LayerNorm ops
+  std::vector<AttnQkvPlan*> atp;     // fused LayerNorm + to_qkv + linear-attention ops
+  float* attn_cs = nullptr;          // [n wmats][384] column sums of the gain-folded to_qkv weights (rows of unused matrices are 0)
   int* t_dev = nullptr;
   float* x_state = nullptr;      // [cap, N, d] running sample
   float* x_tmp = nullptr;        // [cap, N, d] scratch (q_sample / host staging)

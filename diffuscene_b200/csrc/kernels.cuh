@@ -141,6 +141,13 @@ bool ln_gemm_supported(int N, int K);
 LnGemmPlan* ln_plan_create(const GemmArgs& g, int rows_capacity, char* err, int err_len);
 void ln_plan_destroy(LnGemmPlan* p);
 int launch_gemm_ln(const LnGemmPlan* p, int M, cudaStream_t s);
+// fused channel LayerNorm + to_qkv + linear-attention core (gemm_attn.cu)
+struct AttnQkvPlan;
+bool attn_qkv_supported(int n_obj, int C);
+AttnQkvPlan* attn_qkv_plan_create(const void* x, int ldx, const void* w, int ldw, const float* cs, void* o, int ldo,
+                                  int n_obj, int K, int rows_capacity, char* err, int err_len);
+void attn_qkv_plan_destroy(AttnQkvPlan* p);
+int launch_ln_qkv_attn(const AttnQkvPlan* p, int M, cudaStream_t s);
 inline int tc_gnt_row(int stored_row) { const int l = stored_row & 31; return (stored_row & ~31) + 8 * (l & 3) + (l >> 2); }
 
 }  // namespace ds

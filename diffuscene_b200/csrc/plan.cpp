@@ -13,6 +13,7 @@ struct Builder {
   bool no_reuse;
   bool fuse = false;
   bool fuse_ln = false;     // to_out + LayerNorm + residual of the attention wrappers as one op
+  bool fuse_attn = false;   // LayerNorm + to_qkv + linear-attention core as one op
   bool train = false;       // activations as separate ops (the backward pass needs the pre-activation)
   std::map<int, int> zbuf;  // train: output buffer -> buffer of the same width holding the pre-activations
   std::vector<int> refs;
@@ -204,20 +205,33 @@ struct Builder {
   // Residual(PreNorm(LinearAttention)) (denoise_net.py:208-235) / Attention for the mid block (:237-259)
   int self_attn(const std::string& name, int x, bool softmax_kind) {
     const int H = 128;
-    int n1 = new_buf(C);
-    ln(name + ".prenorm", x, n1, vsingle(name + ".fn.norm.g", C), -1);
-    int qkv = new_buf(3 * H);
-    gemm(name + ".to_qkv", full(n1), Slice(), wsingle(name + ".fn.fn.to_qkv.weight", 3 * H, C), -1, 3 * H, 0, -1, qkv,
-         0);
-    release(n1);
-    int o = new_buf(H);
-    {
+    int o;
+    if (fuse_attn && !softmax_kind) {
+      o = new_buf(H);
       Op op;
-      op.kind = softmax_kind ? OP_ATTN : OP_LINATTN;
-      op.name = name + ".core"; op.in0 = full(qkv); op.out = o; op.N = H;
+      op.kind = OP_LN_QKV_ATTN; op.name = name + ".core"; op.in0 = full(x); op.out = o; op.N = H;
+      WRecipe r;
+      r.N = 3 * H; r.K = C; r.scale_k = name + ".fn.norm.g";
+      r.pieces.push_back({name + ".fn.fn.to_qkv.weight", 0, 0, 3 * H, C});
+      expect(r.scale_k, C);
+      op.w = wmat(r);
       p->ops.push_back(op);
+    } else {
+      int n1 = new_buf(C);
+      ln(name + ".prenorm", x, n1, vsingle(name + ".fn.norm.g", C), -1);
+      int qkv = new_buf(3 * H);
+      gemm(name + ".to_qkv", full(n1), Slice(), wsingle(name + ".fn.fn.to_qkv.weight", 3 * H, C), -1, 3 * H, 0, -1, qkv,
+           0);
+      release(n1);
+      o = new_buf(H);
+      {
+        Op op;
+        op.kind = softmax_kind ? OP_ATTN : OP_LINATTN;
+        op.name = name + ".core"; op.in0 = full(qkv); op.out = o; op.N = H;
+        p->ops.push_back(op);
+      }
+      release(qkv);
     }
-    release(qkv);
     int out;
     if (softmax_kind) {
       out = new_buf(C);
@@ -309,6 +323,7 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
            128 / cfg.num_objects <= 10;   // the fused epilogue's coefficient table holds <= 10 scenes per tile
 
   b.fuse_ln = b.fuse && cfg.fuse_level >= 4 && C == 512;
+  b.fuse_attn = b.fuse && cfg.fuse_level >= 5 && C == 512 && cfg.num_objects == 12;
 
   // ---- input + encoder ----
   int xin = b.new_buf(P.kin_pad);
@@ -459,7 +474,7 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
 }
 
 std::string describe_plan(const Plan& p) {
-  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN", "GEMM_GN", "GEMM_LN", "ACT"};
+  static const char* kinds[] = {"PACK", "GEMM", "GN", "LN", "LINATTN", "ATTN", "XATTN", "GEMM_GN", "GEMM_LN", "LN_QKV_ATTN", "ACT"};
   std::ostringstream os;
   os << "plan: C=" << p.C << " d=" << p.d << " kin_pad=" << p.kin_pad << " dpad=" << p.dpad << " buffers="
      << p.buf_width.size() << " ops=" << p.ops.size() << " time_blocks=" << p.time_blocks.size()
@@ -508,7 +523,8 @@ std::string export_plan_json(const Plan& p) {
   os << "],\"wmats\":[";
   for (size_t i = 0; i < p.wmats.size(); ++i) {
     const WRecipe& r = p.wmats[i];
-    os << (i ? "," : "") << "{\"N\":" << r.N << ",\"K\":" << r.K << ",\"ws\":" << (r.ws ? 1 : 0) << ",\"pieces\":[";
+    os << (i ? "," : "") << "{\"N\":" << r.N << ",\"K\":" << r.K << ",\"ws\":" << (r.ws ? 1 : 0) << ",\"scale_k\":\""
+       << r.scale_k << "\",\"pieces\":[";
     for (size_t j = 0; j < r.pieces.size(); ++j) {
       const WPiece& pc = r.pieces[j];
       os << (j ? "," : "") << "{\"name\":\"" << pc.name << "\",\"row_off\":" << pc.row_off << ",\"col_off\":"

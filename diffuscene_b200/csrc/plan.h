@@ -27,6 +27,8 @@ enum OpKind {
   OP_XATTN,         // cross linear-attention apply (q [M,128] x precomputed text context)
   OP_GEMM_GN,       // GEMM with the GroupNorm + affine (+FiLM) + SiLU (+res) epilogue fused (tcgen05 only)
   OP_GEMM_LN,       // GEMM with the channel LayerNorm (gain `gamma`) (+res) epilogue fused (tcgen05 only, fuse_level >= 4)
+  OP_LN_QKV_ATTN,   // channel LayerNorm + to_qkv + linear-attention core in one kernel (fuse_level >= 4, N = 12): the
+                    // weight matrix carries the LayerNorm gain (WRecipe::scale_k), out = o [M, 128]
   OP_ACT,           // train mode only: out[:, out_col : out_col + N] = act(in0) (GELU / SiLU as their own op, pre-activation kept)
 };
 
@@ -51,6 +53,7 @@ struct WPiece { std::string name; int row_off, col_off, rows, cols; };
 struct WRecipe {           // packed matrix [N, K] in the activation dtype
   int N = 0, K = 0;
   bool ws = false;         // weight-standardise each piece (denoise_net.py:83-89)
+  std::string scale_k;     // optional [K] vector multiplied into the columns (a LayerNorm gain folded into the next conv)
   std::vector<WPiece> pieces;
 };
 struct VPiece { std::string name; int off, n; };

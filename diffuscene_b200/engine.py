@@ -43,7 +43,8 @@ class DenoiserEngine:
             # (N = 12 objects), the row-major fused kernel (level 1) otherwise
             # 3: ... and the epilogue-bound plain GEMMs (to_qkv, to_out) on the same kernel
             # 4: ... and to_out + LayerNorm + residual of the attention wrappers as one kernel (k_gemm_ln)
-            fuse_level = 4 if (precision == "bf16" and gemm_backend != "simt") else 0
+            # 5: ... and LayerNorm + to_qkv + linear-attention core as one kernel (k_ln_qkv_attn, N = 12)
+            fuse_level = 5 if (precision == "bf16" and gemm_backend != "simt") else 0
         self.fuse_level = fuse_level
         self.cfg = capi.make_config(spec, num_objects, num_timesteps, _PREC[precision], _BACKEND[gemm_backend],
                                     device, fuse_level)

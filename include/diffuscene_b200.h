@@ -73,7 +73,8 @@ typedef struct ds_config {
                                channels-on-lanes conv+GroupNorm GEMM where supported;
                                3: + epilogue-bound plain GEMMs on that kernel;
                                4: + to_out + LayerNorm + residual of the attention wrappers
-                                  as one GEMM with a LayerNorm epilogue                  */
+                                  as one GEMM with a LayerNorm epilogue;
+                               5: + LayerNorm + to_qkv + linear-attention core as one kernel (N = 12) */
   int32_t train;            /* 1: training step program -- one op per reference layer (no fused epilogues, activations
                                as their own ops), every intermediate kept for the backward pass (ds_train_*)   */
   int32_t reserved[6];

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .unet1d_ref import sinusoidal_embedding
 
-OP_PACK, OP_GEMM, OP_GN, OP_LN, OP_LINATTN, OP_ATTN, OP_XATTN, OP_GEMM_GN, OP_GEMM_LN = range(9)
+OP_PACK, OP_GEMM, OP_GN, OP_LN, OP_LINATTN, OP_ATTN, OP_XATTN, OP_GEMM_GN, OP_GEMM_LN, OP_LN_QKV_ATTN, OP_ACT = range(11)
 
 
 def _r(x, on):
@@ -33,6 +33,8 @@ def assemble_wmat(r, sd):
             var = src.var(dim=1, unbiased=False, keepdim=True)
             src = (src - mean) * torch.rsqrt(var + 1e-5)
         W[pc["row_off"]:pc["row_off"] + pc["rows"], pc["col_off"]:pc["col_off"] + pc["cols"]] = src
+    if r.get("scale_k"):       # a LayerNorm gain folded into the columns (fused LN + to_qkv op)
+        W = W * sd[r["scale_k"]].reshape(1, -1).to(torch.float32)
     return W
 
 
@@ -141,6 +143,17 @@ def run_plan(plan: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.
             if op["res"] >= 0:
                 y = y + bufs[op["res"]]
             bufs[op["out"]] = _r(y, bf)
+        elif k == OP_LN_QKV_ATTN:      # LayerNorm (gain folded into the packed weights) + to_qkv + linear-attention core
+            hh = bufs[i0["buf"]]
+            mean = hh.mean(dim=1, keepdim=True)
+            var = hh.var(dim=1, unbiased=False, keepdim=True)
+            qkv = ((hh - mean) * torch.rsqrt(var + 1e-5)) @ wm[op["w"]].t()
+            q, kk, v = heads(qkv[:, :128]), heads(qkv[:, 128:256]), heads(qkv[:, 256:384])
+            q = q.softmax(dim=-1) * (32 ** -0.5)
+            kk = kk.softmax(dim=1)
+            ctx = torch.einsum("bnhd,bnhe->bhde", kk, v)
+            o = torch.einsum("bhde,bnhd->bnhe", ctx, q)
+            bufs[op["out"]] = _r(o.reshape(M, 128), bf)
         elif k == OP_LINATTN:
             qkv = bufs[i0["buf"]]
             q, kk, v = heads(qkv[:, :128]), heads(qkv[:, 128:256]), heads(qkv[:, 256:384])

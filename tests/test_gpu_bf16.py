@@ -84,7 +84,7 @@ def test_fused_groupnorm_epilogue_matches_unfused(name, golden_dir):
     assert (a - g).abs().mean() <= (b - g).abs().mean() * 1.5 + 1e-4
 
 
-@pytest.mark.parametrize("fuse", [2, 3, 4])
+@pytest.mark.parametrize("fuse", [2, 3, 4, 5])
 @pytest.mark.parametrize("name", ["bed62", "bed97", "text62", "arr5", "obj29"])
 def test_channels_on_lanes_groupnorm_gemm(name, fuse, golden_dir):
     """fuse_level 2 (the conv + GroupNorm GEMM with the output channels on the TMEM lanes, weights stored
@@ -92,7 +92,8 @@ def test_channels_on_lanes_groupnorm_gemm(name, fuse, golden_dir):
     uniform-free per-scene FiLM (forward with per-scene t), the per-object FiLM of the context blocks, the
     two-operand skip convs and the residual path.  fuse_level 3 also routes every plain GEMM with N % 128 == 0
     (encoder / decoder MLPs, qkv, to_out, res_conv, down / up convs) to the same kernel; fuse_level 4 fuses to_out +
-    LayerNorm + residual of every (cross-)attention wrapper into k_gemm_ln.  Cases with N != 12 objects keep the
+    LayerNorm + residual of every (cross-)attention wrapper into k_gemm_ln; fuse_level 5 fuses LayerNorm + to_qkv + the
+    linear-attention core into k_ln_qkv_attn (N = 12).  Cases with N != 12 objects keep the
     row-major kernels."""
     e2, case, spec, inp = get_engine(name, "bf16", "tcgen05", fuse=fuse)
     e1, _, _, _ = get_engine(name, "bf16", "tcgen05", fuse=1)
