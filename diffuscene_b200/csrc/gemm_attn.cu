@@ -319,15 +319,27 @@ k_ln_qkv_attn(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = tile * Cfg::ROWS;
       const int rows_here = min(Cfg::ROWS, epi.M - m0);
-      // ---- (a) LayerNorm statistics of this tile's rows, 8 rows per warp, coalesced 1 KB row reads
-      for (int r = ew * 8; r < ew * 8 + 8; ++r) {
-        float s = 0.f, ss = 0.f;
-        if (r < rows_here) {
-          const uint4* rp = reinterpret_cast<const uint4*>(epi.x + (int64_t)(m0 + r) * epi.ldx) + lane * 2;
+      // ---- (a) LayerNorm statistics of this tile's rows, 8 rows per warp, coalesced 1 KB row reads; the loads of four
+      //      rows are in flight together (one L2 round trip per batch instead of one per row)
+#pragma unroll
+      for (int rb = 0; rb < 8; rb += 4) {
+        uint4 u[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = ew * 8 + rb + j;
+          u[j][0] = u[j][1] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < rows_here) {
+            const uint4* rp = reinterpret_cast<const uint4*>(epi.x + (int64_t)(m0 + r) * epi.ldx) + lane * 2;
+            u[j][0] = __ldg(rp);
+            u[j][1] = __ldg(rp + 1);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float s = 0.f, ss = 0.f;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            const uint4 u = __ldg(rp + i);
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            const uint32_t w4[4] = {u[j][i].x, u[j][i].y, u[j][i].z, u[j][i].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float a = __uint_as_float(w4[e] << 16), b = __uint_as_float(w4[e] & 0xffff0000u);
@@ -336,13 +348,13 @@ k_ln_qkv_attn(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
               ss = fmaf(b, b, ss);
             }
           }
-        }
-        s = warp_sum(s);
-        ss = warp_sum(ss);
-        if (lane == 0) {
-          const float mean = s * (1.0f / 512.0f);
-          const float var = fmaxf(ss * (1.0f / 512.0f) - mean * mean, 0.f);
-          stat_s[r] = make_float2(mean, rsqrtf(var + 1e-5f));
+          s = warp_sum(s);
+          ss = warp_sum(ss);
+          if (lane == 0) {
+            const float mean = s * (1.0f / 512.0f);
+            const float var = fmaxf(ss * (1.0f / 512.0f) - mean * mean, 0.f);
+            stat_s[ew * 8 + rb + j] = make_float2(mean, rsqrtf(var + 1e-5f));
+          }
         }
       }
       epi_bar();                                  // statistics visible; every warp has left the previous tile's core

@@ -21,6 +21,10 @@ run_task() {
     bench)
       timeout 900 python bench.py "$@" > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
       tail -c 1500 gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json ;;
+    benchn)           # benchn <name> [bench args]: like bench, output in gpurun_out/<tag>_bench_<name>.json
+      local nm=$1; shift
+      timeout 900 python bench.py "$@" > gpurun_out/${TAG}_bench_${nm}.json 2> gpurun_out/${TAG}_bench_${nm}.err
+      tail -c 600 gpurun_out/${TAG}_bench_${nm}.err; cut -c1-420 gpurun_out/${TAG}_bench_${nm}.json ;;
     ops)
       timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-ops "$@" 2> gpurun_out/${TAG}_per_op_us.txt | cut -c1-300
       tail -n +1 gpurun_out/${TAG}_per_op_us.txt | head -150 ;;
