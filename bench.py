@@ -456,7 +456,7 @@ def main():
                 tj = json.load(f)
             res["roofline"]["traffic"] = tj["step_dram_bytes"]
             res["roofline"]["traffic_source"] = "profiles/%s (ncu dram__bytes_read+write, one step)" % os.path.basename(tpath)
-            k = tj["kernels"].get("k_gemm_gnt<%d>" % N_OBJ)
+            k = next((v for n, v in tj["kernels"].items() if n.startswith("k_gemm_gnt<%d" % N_OBJ)), None)
             if k and dom:
                 res["roofline"]["dominant_kernel"]["traffic"] = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"]
                 res["roofline"]["dominant_kernel"]["ncu_share_of_step"] = k["time_ns"] / tj["step_time_ns"]
