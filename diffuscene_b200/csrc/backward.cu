@@ -11,6 +11,8 @@
 //   weights         k_ws_unpack: packed-matrix gradients -> named tensors through the weight-standardisation adjoint
 //   optimizer       k_adam, k_sumsq (global gradient norm for clip_grad_norm_)
 // Storage type T is float (parity mode) or bf16; all arithmetic and every gradient w.r.t. a parameter is fp32.
+#include <stdlib.h>
+
 #include "../../include/diffuscene_b200.h"
 #include "kernels.cuh"
 
@@ -215,6 +217,170 @@ void launch_act_bwd(const T* z, int ldz, const T* dy, int ldy, T* dz, int lddz, 
   if (n > 0) k_act_bwd<T><<<cdiv64(n, 256), 256, 0, s>>>(z, ldz, dy, ldy, dz, lddz, M, N, act);
 }
 
+// ---- register-resident variants for the shipped shapes (64 channels per group, N = 12 / 21 objects) -----------------
+// A warp owns one (scene, group) and a lane owns the channel pair (2 lane, 2 lane + 1) of the group for ALL tokens of
+// the scene: the group is read from HBM exactly once into registers (4-byte bf16x2 / 8-byte float2 loads, 128 / 256 B
+// per warp instruction), statistics, adjoint sums and outputs are computed from registers.  The generic kernels above
+// make three passes over global memory; these are bound by one read and one write of the activation.
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct Pair<bf16> {
+  static __device__ __forceinline__ float2 ld(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+  static __device__ __forceinline__ void st(bf16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+};
+__device__ __forceinline__ const float* film_row(const FilmRef& film, int scene, int r, int64_t row) {
+  if (film.mode == FILM_TIME) return film.base + (int64_t)film.t[scene] * film.row_stride;
+  if (film.mode == FILM_OBJECT) return film.base + (int64_t)r * film.row_stride;
+  if (film.mode == FILM_TOKEN) return film.base + row * film.row_stride;
+  return nullptr;
+}
+
+template <typename T, int NOBJ>
+__global__ void __launch_bounds__(256) k_gn_fwd_reg(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    FilmRef film, const T* __restrict__ res, int ld_res, int n_scenes, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_scenes * 8) return;
+  const int scene = warp >> 3, grp = warp & 7, ch = grp * 64 + 2 * lane;
+  const int64_t row0 = (int64_t)scene * NOBJ;
+  float2 v[NOBJ];
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < NOBJ; ++r) {
+    v[r] = Pair<T>::ld(in + (row0 + r) * ld_in + ch);
+    s += v[r].x + v[r].y;
+  }
+  const float inv = 1.0f / float(NOBJ * 64);
+  const float mean = warp_sum(s) * inv;
+  float q = 0.f;
+#pragma unroll
+  for (int r = 0; r < NOBJ; ++r) {
+    const float a = v[r].x - mean, b = v[r].y - mean;
+    q = fmaf(a, a, q);
+    q = fmaf(b, b, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * inv + 1e-5f);
+  const float2 ga = *reinterpret_cast<const float2*>(gamma + ch), be = *reinterpret_cast<const float2*>(beta + ch);
+#pragma unroll
+  for (int r = 0; r < NOBJ; ++r) {
+    const int64_t row = row0 + r;
+    float2 y = make_float2(fmaf((v[r].x - mean) * rstd, ga.x, be.x), fmaf((v[r].y - mean) * rstd, ga.y, be.y));
+    if (const float* fr = film_row(film, scene, r, row)) {
+      const float2 sc = *reinterpret_cast<const float2*>(fr + ch), sh = *reinterpret_cast<const float2*>(fr + C + ch);
+      y = make_float2(fmaf(y.x, sc.x + 1.0f, sh.x), fmaf(y.y, sc.y + 1.0f, sh.y));
+    }
+    y = make_float2(silu_exact(y.x), silu_exact(y.y));
+    if (res) {
+      const float2 rv = Pair<T>::ld(res + row * ld_res + ch);
+      y.x += rv.x;
+      y.y += rv.y;
+    }
+    Pair<T>::st(out + row * ld_out + ch, y);
+  }
+}
+
+template <typename T, int NOBJ>
+__global__ void __launch_bounds__(256) k_gn_bwd_reg(const T* __restrict__ c, int ldc, const T* __restrict__ dy, int ldy,
+                                                    T* __restrict__ dc, int lddc, T* __restrict__ dres, int ldr,
+                                                    int res_accumulate, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, FilmRef film, float* __restrict__ dgamma,
+                                                    float* __restrict__ dbeta, float* __restrict__ dfilm,
+                                                    int64_t dfilm_row_stride, int n_scenes, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_scenes * 8) return;
+  const int scene = warp >> 3, grp = warp & 7, ch = grp * 64 + 2 * lane;
+  const int64_t row0 = (int64_t)scene * NOBJ;
+  float2 xh[NOBJ], gy[NOBJ];
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < NOBJ; ++r) {
+    xh[r] = Pair<T>::ld(c + (row0 + r) * ldc + ch);
+    gy[r] = Pair<T>::ld(dy + (row0 + r) * ldy + ch);
+    s += xh[r].x + xh[r].y;
+  }
+  const float inv = 1.0f / float(NOBJ * 64);
+  const float mean = warp_sum(s) * inv;
+  float q = 0.f;
+#pragma unroll
+  for (int r = 0; r < NOBJ; ++r) {
+    xh[r].x -= mean;
+    xh[r].y -= mean;
+    q = fmaf(xh[r].x, xh[r].x, q);
+    q = fmaf(xh[r].y, xh[r].y, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * inv + 1e-5f);
+  const float2 ga = *reinterpret_cast<const float2*>(gamma + ch), be = *reinterpret_cast<const float2*>(beta + ch);
+  float2 dga = make_float2(0.f, 0.f), dbe = dga, dsc = dga, dsh = dga;
+  float g1 = 0.f, g2 = 0.f;
+  // gy[r] is turned into dxhat in place; the residual passthrough leaves first
+#pragma unroll
+  for (int r = 0; r < NOBJ; ++r) {
+    const int64_t row = row0 + r;
+    if (dres) {
+      T* p = dres + row * ldr + ch;
+      float2 o = gy[r];
+      if (res_accumulate) {
+        const float2 old = Pair<T>::ld(p);
+        o.x += old.x;
+        o.y += old.y;
+      }
+      Pair<T>::st(p, o);
+    }
+    xh[r].x *= rstd;
+    xh[r].y *= rstd;
+    const float2 u = make_float2(fmaf(xh[r].x, ga.x, be.x), fmaf(xh[r].y, ga.y, be.y));
+    float2 sc = make_float2(1.0f, 1.0f), sh = make_float2(0.f, 0.f);
+    if (const float* fr = film_row(film, scene, r, row)) {
+      const float2 a = *reinterpret_cast<const float2*>(fr + ch);
+      sc = make_float2(a.x + 1.0f, a.y + 1.0f);
+      sh = *reinterpret_cast<const float2*>(fr + C + ch);
+    }
+    const float2 dw = make_float2(gy[r].x * act_grad(fmaf(u.x, sc.x, sh.x), ACT_SILU), gy[r].y * act_grad(fmaf(u.y, sc.y, sh.y), ACT_SILU));
+    if (film.mode == FILM_TIME) {
+      dsc.x = fmaf(dw.x, u.x, dsc.x); dsc.y = fmaf(dw.y, u.y, dsc.y);
+      dsh.x += dw.x; dsh.y += dw.y;
+    } else if (film.mode == FILM_OBJECT) {
+      atomicAdd(dfilm + (int64_t)r * dfilm_row_stride + ch, dw.x * u.x);
+      atomicAdd(dfilm + (int64_t)r * dfilm_row_stride + ch + 1, dw.y * u.y);
+      atomicAdd(dfilm + (int64_t)r * dfilm_row_stride + C + ch, dw.x);
+      atomicAdd(dfilm + (int64_t)r * dfilm_row_stride + C + ch + 1, dw.y);
+    } else if (film.mode == FILM_TOKEN) {
+      *reinterpret_cast<float2*>(dfilm + row * dfilm_row_stride + ch) = make_float2(dw.x * u.x, dw.y * u.y);
+      *reinterpret_cast<float2*>(dfilm + row * dfilm_row_stride + C + ch) = dw;
+    }
+    const float2 du = make_float2(dw.x * sc.x, dw.y * sc.y);
+    dga.x = fmaf(du.x, xh[r].x, dga.x); dga.y = fmaf(du.y, xh[r].y, dga.y);
+    dbe.x += du.x; dbe.y += du.y;
+    gy[r] = make_float2(du.x * ga.x, du.y * ga.y);      // dxhat
+    g1 += gy[r].x + gy[r].y;
+    g2 = fmaf(gy[r].x, xh[r].x, g2);
+    g2 = fmaf(gy[r].y, xh[r].y, g2);
+  }
+  atomicAdd(dgamma + ch, dga.x); atomicAdd(dgamma + ch + 1, dga.y);
+  atomicAdd(dbeta + ch, dbe.x); atomicAdd(dbeta + ch + 1, dbe.y);
+  if (film.mode == FILM_TIME) {
+    *reinterpret_cast<float2*>(dfilm + (int64_t)scene * dfilm_row_stride + ch) = dsc;
+    *reinterpret_cast<float2*>(dfilm + (int64_t)scene * dfilm_row_stride + C + ch) = dsh;
+  }
+  g1 = warp_sum(g1) * inv;
+  g2 = warp_sum(g2) * inv;
+#pragma unroll
+  for (int r = 0; r < NOBJ; ++r)
+    Pair<T>::st(dc + (row0 + r) * lddc + ch, make_float2(rstd * (gy[r].x - g1 - xh[r].x * g2), rstd * (gy[r].y - g1 - xh[r].y * g2)));
+}
+template <typename T>
+bool launch_gn_fwd_reg(const T* in, int ld_in, T* out, int ld_out, const float* gamma, const float* beta, FilmRef film,
+                       const T* res, int ld_res, int n_scenes, int n_obj, int C, int groups, cudaStream_t s) {
+  if (groups != 8 || C != 512 || (n_obj != 12 && n_obj != 21) || n_scenes <= 0) return false;
+  const int64_t warps = (int64_t)n_scenes * 8;
+  if (n_obj == 12) k_gn_fwd_reg<T, 12><<<cdiv64(warps, 8), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, film, res, ld_res, n_scenes, C);
+  else k_gn_fwd_reg<T, 21><<<cdiv64(warps, 8), 256, 0, s>>>(in, ld_in, out, ld_out, gamma, beta, film, res, ld_res, n_scenes, C);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block backward: y = SiLU( (GN(c) * gamma + beta) * (scale + 1) + shift ) (+ res)        (denoise_net.py:160-176)
 // one warp per (scene, group of C / 8 channels): lane <-> channels lane, lane + 32 of the group, loop over the tokens
@@ -313,7 +479,15 @@ void launch_gn_bwd(const T* c, int ldc, const T* dy, int ldy, T* dc, int lddc, T
                    const float* gamma, const float* beta, FilmRef film, float* dgamma, float* dbeta, float* dfilm,
                    int64_t dfilm_row_stride, int n_scenes, int n_obj, int C, int groups, cudaStream_t s) {
   const int64_t warps = (int64_t)n_scenes * groups;
-  if (warps > 0)
+  if (warps <= 0) return;
+  static const int use_reg = getenv("DS_GN_REG") ? atoi(getenv("DS_GN_REG")) : 1;
+  if (use_reg && groups == 8 && C == 512 && n_obj == 12)
+    k_gn_bwd_reg<T, 12><<<cdiv64(warps, 8), 256, 0, s>>>(c, ldc, dy, ldy, dc, lddc, dres, ldr, res_accumulate, gamma, beta, film,
+                                                         dgamma, dbeta, dfilm, dfilm_row_stride, n_scenes, C);
+  else if (use_reg && groups == 8 && C == 512 && n_obj == 21)
+    k_gn_bwd_reg<T, 21><<<cdiv64(warps, 8), 256, 0, s>>>(c, ldc, dy, ldy, dc, lddc, dres, ldr, res_accumulate, gamma, beta, film,
+                                                         dgamma, dbeta, dfilm, dfilm_row_stride, n_scenes, C);
+  else
     k_gn_bwd<T><<<cdiv64(warps, 8), 256, 0, s>>>(c, ldc, dy, ldy, dc, lddc, dres, ldr, res_accumulate, gamma, beta, film,
                                                  dgamma, dbeta, dfilm, dfilm_row_stride, n_scenes, n_obj, C, groups);
 }
@@ -847,6 +1021,8 @@ void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float 
   template void launch_act_bwd<T>(const T*, int, const T*, int, T*, int, int, int, int, cudaStream_t);                \
   template void launch_gn_bwd<T>(const T*, int, const T*, int, T*, int, T*, int, int, const float*, const float*,     \
                                  FilmRef, float*, float*, float*, int64_t, int, int, int, int, cudaStream_t);         \
+  template bool launch_gn_fwd_reg<T>(const T*, int, T*, int, const float*, const float*, FilmRef, const T*, int, int, int,   \
+                                     int, int, cudaStream_t);                                                         \
   template void launch_ln_bwd<T>(const T*, int, const T*, int, T*, int, int, T*, int, int, const float*, float*, int, \
                                  int, cudaStream_t);                                                                  \
   template void launch_linattn_bwd<T>(const T*, int, const T*, int, T*, int, int, int, cudaStream_t);                 \

@@ -51,7 +51,9 @@ constexpr uint32_t AT_IDESC_128 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t
 
 template <int NOBJ>
 struct AtCfg {
-  static constexpr int SPT = (NOBJ == 12) ? 10 : 128 / NOBJ;        // scenes per tile
+  // scenes per tile: 10 x 12 = 120 rows; for N = 21 five scenes (105 rows): six would not leave shared memory for the
+  // 11 masked tail rows of the last scene's second 16-token MMA step
+  static constexpr int SPT = (NOBJ == 12) ? 10 : (NOBJ == 21 ? 5 : 128 / NOBJ);
   static constexpr int ROWS = SPT * NOBJ;                            // token rows per tile (<= 128)
   static constexpr int NT = (NOBJ + 15) / 16 * 16;                   // tokens of a scene rounded up to MMA tiles
   static constexpr int STG_ROWS = ROWS + (NT - NOBJ);                // + zeroed tail rows read (masked) by the last scene
@@ -424,7 +426,7 @@ bool tc_encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t r
 int* tc_error_flag_dev();
 int tc_num_sms();
 
-bool attn_qkv_supported(int n_obj, int C) { return n_obj == 12 && C == 512; }
+bool attn_qkv_supported(int n_obj, int C) { return (n_obj == 12 || n_obj == 21) && C == 512; }
 
 // x [rows, 512] bf16; w [384, 512] bf16 = to_qkv weights with the LayerNorm gain folded into the columns;
 // cs [384] fp32 = row sums of those (bf16-rounded) weights; o [rows, 128] bf16
@@ -432,12 +434,13 @@ AttnQkvPlan* attn_qkv_plan_create(const void* x, int ldx, const void* w, int ldw
                                   int n_obj, int K, int rows_capacity, char* err, int err_len) {
   if (!tc_runtime_available(err, err_len)) return nullptr;
   if (!attn_qkv_supported(n_obj, K) || (ldx % 8) || (ldw % 8) || (ldo % 2)) {
-    if (err) snprintf(err, err_len, "fused LN + to_qkv + linear attention needs n_obj = 12, C = 512, aligned pitches");
+    if (err) snprintf(err, err_len, "fused LN + to_qkv + linear attention needs n_obj in {12, 21}, C = 512, aligned pitches");
     return nullptr;
   }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_ln_qkv_attn<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<12>::SMEM);
+    cudaFuncSetAttribute(k_ln_qkv_attn<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<21>::SMEM);
     attr_set = true;
   }
   AttnQkvPlan* p = new AttnQkvPlan();
@@ -465,10 +468,12 @@ int launch_ln_qkv_attn(const AttnQkvPlan* p, int M, cudaStream_t s) {
   AtEpi epi = p->epi;
   epi.M = M;
   const int n_scenes = M / p->n_obj;
-  const int tiles = (n_scenes + AtCfg<12>::SPT - 1) / AtCfg<12>::SPT;
+  const int spt = p->n_obj == 21 ? AtCfg<21>::SPT : AtCfg<12>::SPT;
+  const int tiles = (n_scenes + spt - 1) / spt;
   if (tiles == 0) return 0;
   const int grid = tiles < p->num_sms ? tiles : p->num_sms;
-  k_ln_qkv_attn<12><<<grid, AT_THREADS, AtCfg<12>::SMEM, s>>>(p->tm_x, p->tm_w, epi, tc_error_flag_dev());
+  if (p->n_obj == 21) k_ln_qkv_attn<21><<<grid, AT_THREADS, AtCfg<21>::SMEM, s>>>(p->tm_x, p->tm_w, epi, tc_error_flag_dev());
+  else k_ln_qkv_attn<12><<<grid, AT_THREADS, AtCfg<12>::SMEM, s>>>(p->tm_x, p->tm_w, epi, tc_error_flag_dev());
   return (int)cudaGetLastError();
 }
 

@@ -323,7 +323,7 @@ bool build_plan(const ds_config& cfg, bool no_reuse, Plan* plan) {
            128 / cfg.num_objects <= 10;   // the fused epilogue's coefficient table holds <= 10 scenes per tile
 
   b.fuse_ln = b.fuse && cfg.fuse_level >= 4 && C == 512;
-  b.fuse_attn = b.fuse && cfg.fuse_level >= 5 && C == 512 && cfg.num_objects == 12;
+  b.fuse_attn = b.fuse && cfg.fuse_level >= 5 && C == 512 && (cfg.num_objects == 12 || cfg.num_objects == 21);
 
   // ---- input + encoder ----
   int xin = b.new_buf(P.kin_pad);

@@ -25,6 +25,9 @@ void launch_gn_bwd(const T* c, int ldc, const T* dy, int ldy, T* dc, int lddc, T
                    const float* gamma, const float* beta, FilmRef film, float* dgamma, float* dbeta, float* dfilm,
                    int64_t dfilm_row_stride, int n_scenes, int n_obj, int C, int groups, cudaStream_t s);
 template <typename T>
+bool launch_gn_fwd_reg(const T* in, int ld_in, T* out, int ld_out, const float* gamma, const float* beta, FilmRef film,
+                       const T* res, int ld_res, int n_scenes, int n_obj, int C, int groups, cudaStream_t s);
+template <typename T>
 void launch_ln_bwd(const T* x, int ldx, const T* dy, int ldy, T* dx, int lddx, int dx_accumulate, T* dres, int ldr,
                    int res_accumulate, const float* g, float* dg, int M, int C, cudaStream_t s);
 template <typename T> void launch_linattn_bwd(const T* qkv, int ld, const T* dout, int ldo, T* dqkv, int lddq, int n_scenes, int N, cudaStream_t s);
@@ -50,6 +53,47 @@ __global__ void k_vec_add(float* __restrict__ dst, const float* __restrict__ src
 __global__ void k_iota(int* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = i;
+}
+// fp32 [B, cols] (row pitch ld) -> bf16 copy (row pitch ldo) for rows < B
+__global__ void k_f32_to_bf16(const float* __restrict__ in, int ld, ds::bf16* __restrict__ out, int ldo, int B, int cols) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * cols) return;
+  const int b = int(i / cols), c = int(i % cols);
+  out[(int64_t)b * ldo + c] = __float2bfloat16_rn(in[(int64_t)b * ld + c]);
+}
+__global__ void k_bf16_to_f32(const ds::bf16* __restrict__ in, int ld, float* __restrict__ out, int ldo, int B, int cols) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * cols) return;
+  const int b = int(i / cols), c = int(i % cols);
+  out[(int64_t)b * ldo + c] = __bfloat162float(in[(int64_t)b * ld + c]);
+}
+// d(FiLM) of one time block: fp32 [B, cols] -> bf16 copy (for dX), bf16 transpose [cols, Bp] zero-padded (for dW), and
+// the column sums (bias gradient), one pass
+__global__ void k_dfilm_prepare(const float* __restrict__ in, int ld, ds::bf16* __restrict__ out, int ldo,
+                                ds::bf16* __restrict__ outT, int Bp, int B, int cols, float* __restrict__ colsum) {
+  __shared__ float tile[32][33];
+  __shared__ float part[8][33];
+  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  float cs = 0.f;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int m = m0 + i, c = c0 + threadIdx.x;
+    const float v = (m < B && c < cols) ? in[(int64_t)m * ld + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    cs += v;
+    if (m < B && c < cols) out[(int64_t)m * ldo + c] = __float2bfloat16_rn(v);
+  }
+  part[threadIdx.y][threadIdx.x] = cs;
+  __syncthreads();
+  if (threadIdx.y == 0 && c0 + threadIdx.x < cols && m0 < B) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tsum += part[y][threadIdx.x];
+    atomicAdd(colsum + c0 + threadIdx.x, tsum);
+  }
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, m = m0 + threadIdx.x;
+    if (c < cols && m < Bp) outT[(int64_t)c * Bp + m] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
 }
 // dst = src * act'(z) elementwise (fp32 conditioning path)
 __global__ void k_mul_actgrad(const float* __restrict__ g, const float* __restrict__ z, float* __restrict__ out, int64_t n, int act) {
@@ -101,6 +145,15 @@ struct TrainState {
   std::vector<TcGemmPlan*> tc_fwd;
   std::vector<TcGemmPlan*> tc_dx[2], tc_dw[2];
   ds::bf16 *trA = nullptr, *trB = nullptr;
+  // time-FiLM projections on the tensor cores (bf16 mode): [B, 4C] x 19 x [2C, 4C]
+  int Bp = 0;
+  ds::bf16 *st_bf = nullptr, *film_bf = nullptr, *dfilm_bf = nullptr, *dst_bf = nullptr, *wall_bf = nullptr,
+           *wallT_bf = nullptr, *trF = nullptr, *stT = nullptr;
+  float* ball = nullptr;
+  std::vector<TcGemmPlan*> tc_film;      // forward, one per <= 4096-column chunk
+  std::vector<int> tc_film_n0;
+  TcGemmPlan* tc_dst = nullptr;
+  std::vector<TcGemmPlan*> tc_dwf;       // dW of every time block (split-K, fp32 atomics straight into the flat gradients)
   // gradient buckets for the overlapped data-parallel all-reduce: bucket k = flat range [bounds[k], bounds[k + 1]);
   // its event is recorded as soon as every parameter gradient inside it is final (the backward pass finalises the
   // flat buffer from its END towards its start: parameters are laid out in forward order)
@@ -126,6 +179,11 @@ void train_state_destroy(TrainState* t) {
     for (auto* p : t->tc_dw[k]) if (p) tc_plan_destroy(p);
   }
   cudaFree(t->wtarena); cudaFree(t->trA); cudaFree(t->trB);
+  for (auto* p : t->tc_film) if (p) tc_plan_destroy(p);
+  for (auto* p : t->tc_dwf) if (p) tc_plan_destroy(p);
+  if (t->tc_dst) tc_plan_destroy(t->tc_dst);
+  for (ds::bf16* p : {t->st_bf, t->film_bf, t->dfilm_bf, t->dst_bf, t->wall_bf, t->wallT_bf, t->trF, t->stT}) cudaFree(p);
+  cudaFree(t->ball);
   delete t;
 }
 
@@ -303,6 +361,61 @@ static int train_capacity(ds_handle* h, int n_scenes, int ctx_rows) {
         }
       }
     }
+    if (t->use_tc) {
+      const int W4 = 4 * C, NF = int(P.time_blocks.size()) * 2 * C;
+      t->Bp = train_round_up(n_scenes, 128);
+      for (auto* p : t->tc_film) if (p) tc_plan_destroy(p);
+      for (auto* p : t->tc_dwf) if (p) tc_plan_destroy(p);
+      if (t->tc_dst) tc_plan_destroy(t->tc_dst);
+      t->tc_film.clear(); t->tc_film_n0.clear(); t->tc_dwf.clear(); t->tc_dst = nullptr;
+      for (ds::bf16** p : {&t->st_bf, &t->film_bf, &t->dfilm_bf, &t->dst_bf, &t->wall_bf, &t->wallT_bf, &t->trF, &t->stT}) {
+        cudaFree(*p);
+        *p = nullptr;
+      }
+      cudaFree(t->ball); t->ball = nullptr;
+      auto alloc0 = [&](ds::bf16** p, size_t n) { cudaError_t e = cudaMalloc(p, n * 2); if (e == cudaSuccess) e = cudaMemset(*p, 0, n * 2); return e; };
+      CK(alloc0(&t->st_bf, (size_t)t->Bp * W4));
+      CK(alloc0(&t->film_bf, (size_t)t->Bp * NF));
+      CK(alloc0(&t->dfilm_bf, (size_t)t->Bp * NF));
+      CK(alloc0(&t->dst_bf, (size_t)t->Bp * W4));
+      CK(alloc0(&t->wall_bf, (size_t)NF * W4));
+      CK(alloc0(&t->wallT_bf, (size_t)W4 * NF));
+      CK(alloc0(&t->trF, (size_t)NF * t->Bp));
+      CK(alloc0(&t->stT, (size_t)W4 * t->Bp));
+      CK(cudaMalloc(&t->ball, (size_t)NF * 4));
+      char err[256] = "";
+      GemmArgs g;
+      for (int n0 = 0; n0 < NF; n0 += 4096) {
+        const int nn = std::min(4096, NF - n0);
+        memset(&g, 0, sizeof g);
+        g.a0 = t->st_bf; g.lda0 = W4; g.k0 = W4;
+        g.w = t->wall_bf + (size_t)n0 * W4; g.ldw = W4;
+        g.bias = t->ball + n0;
+        g.d = t->film_bf + n0; g.ldd = NF;
+        g.M = t->Bp; g.N = nn;
+        TcGemmPlan* p = tc_plan_create(g, t->Bp, err, sizeof err);
+        if (!p) return fail(DS_ERR_CUDA, "train: FiLM projection plan failed: %s", err);
+        t->tc_film.push_back(p);
+        t->tc_film_n0.push_back(n0);
+      }
+      memset(&g, 0, sizeof g);
+      g.a0 = t->dfilm_bf; g.lda0 = NF; g.k0 = NF;
+      g.w = t->wallT_bf; g.ldw = NF;
+      g.d = t->dst_bf; g.ldd = W4;
+      g.M = t->Bp; g.N = W4;
+      t->tc_dst = tc_plan_create(g, t->Bp, err, sizeof err);
+      if (!t->tc_dst) return fail(DS_ERR_CUDA, "train: d(time embedding) plan failed: %s", err);
+      for (size_t i = 0; i < P.time_blocks.size(); ++i) {
+        memset(&g, 0, sizeof g);
+        g.a0 = t->trF + i * (size_t)2 * C * t->Bp; g.lda0 = t->Bp; g.k0 = t->Bp;
+        g.w = t->stT; g.ldw = t->Bp;
+        g.d = t->trF; g.ldd = 8;
+        g.M = 2 * C; g.N = W4;
+        TcGemmPlan* p = tc_plan_create(g, 2 * C, err, sizeof err);
+        if (!p) return fail(DS_ERR_CUDA, "train: FiLM weight-gradient plan failed: %s", err);
+        t->tc_dwf.push_back(p);
+      }
+    }
     t->cap_scenes = n_scenes;
   }
   if (ctx_rows > t->ctx_rows_cap) {
@@ -376,9 +489,27 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
   launch_act<float>(t->z1, 4 * C, t->h1, 4 * C, B, 4 * C, ACT_GELU, s);
   f32gemm(t->h1, 4 * C, 4 * C, F("time_mlp.3.weight"), F("time_mlp.3.bias"), t->temb, 4 * C, 4 * C, B);
   launch_act<float>(t->temb, 4 * C, t->st, 4 * C, B, 4 * C, ACT_SILU, s);
-  for (int i = 0; i < ntb; ++i)
-    f32gemm(t->st, 4 * C, 4 * C, F(P.time_blocks[i] + ".mlp.1.weight"), F(P.time_blocks[i] + ".mlp.1.bias"),
-            t->film + (size_t)i * 2 * C, ntb * 2 * C, 2 * C, B);
+  const bool film_tc = t->use_tc && !t->tc_film.empty();
+  if (film_tc) {
+    // the 19 time-FiLM projections [B, 4C] -> [B, 19 x 2C] on the tensor cores: bf16 copies of SiLU(temb) and of the
+    // block weights (plus their transposes for d(temb)), fp32 accumulation, result widened back to the fp32 table
+    const int W4 = 4 * C, NF = ntb * 2 * C;
+    for (int i = 0; i < ntb; ++i) {
+      launch_pack_piece<bf16>(F(P.time_blocks[i] + ".mlp.1.weight"), 2 * C, W4, t->wall_bf + (size_t)i * 2 * C * W4, W4, 0,
+                              t->wallT_bf + (size_t)i * 2 * C, NF, s);
+      CK(cudaMemcpyAsync(t->ball + (size_t)i * 2 * C, F(P.time_blocks[i] + ".mlp.1.bias"), (size_t)2 * C * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    k_f32_to_bf16<<<((int64_t)B * W4 + 255) / 256, 256, 0, s>>>(t->st, W4, t->st_bf, W4, B, W4);
+    for (auto* p : t->tc_film) {
+      int e = launch_gemm_tc(p, t->Bp, s);
+      if (e) return fail(DS_ERR_CUDA, "train: FiLM projection GEMM failed: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    k_bf16_to_f32<<<((int64_t)B * NF + 255) / 256, 256, 0, s>>>(t->film_bf, NF, t->film, NF, B, NF);
+  } else {
+    for (int i = 0; i < ntb; ++i)
+      f32gemm(t->st, 4 * C, 4 * C, F(P.time_blocks[i] + ".mlp.1.weight"), F(P.time_blocks[i] + ".mlp.1.bias"),
+              t->film + (size_t)i * 2 * C, ntb * 2 * C, 2 * C, B);
+  }
   launch_act<float>(context, E, t->ctx_act, E, ctx_rows, E, ACT_SILU, s);
   for (int i = 0; i < ncb; ++i)
     f32gemm(t->ctx_act, E, E, F(P.ctx_blocks[i] + ".mlp.1.weight"), F(P.ctx_blocks[i] + ".mlp.1.bias"),
@@ -421,8 +552,10 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
         launch_act<T>(ptr(o.in0.buf, o.in0.col), ld(o.in0.buf), ptr(o.out, o.out_col), ld(o.out), M, o.N, o.act, s);
         break;
       case OP_GN:
-        launch_groupnorm<T>(ptr(o.in0.buf, 0), ld(o.in0.buf), ptr(o.out, 0), ld(o.out), t->varena + t->v_off[o.gamma],
-                            t->varena + t->v_off[o.beta], film_of(o), ptr(o.res, 0), ld(o.res), B, n_obj, C, 8, s);
+        if (!launch_gn_fwd_reg<T>(ptr(o.in0.buf, 0), ld(o.in0.buf), ptr(o.out, 0), ld(o.out), t->varena + t->v_off[o.gamma],
+                                  t->varena + t->v_off[o.beta], film_of(o), ptr(o.res, 0), ld(o.res), B, n_obj, C, 8, s))
+          launch_groupnorm<T>(ptr(o.in0.buf, 0), ld(o.in0.buf), ptr(o.out, 0), ld(o.out), t->varena + t->v_off[o.gamma],
+                              t->varena + t->v_off[o.beta], film_of(o), ptr(o.res, 0), ld(o.res), B, n_obj, C, 8, s);
         break;
       case OP_LN:
         launch_layernorm<T>(ptr(o.in0.buf, 0), ld(o.in0.buf), ptr(o.out, 0), ld(o.out), t->varena + t->v_off[o.b],
@@ -523,8 +656,28 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
     return 0;
   };
   bool dst_started = false, dctx_started = false;
+  bool stT_ready = false;
   auto time_block_bwd = [&](int i) {      // FiLM projection of time block i: dW, db, and its share of d(SiLU(temb))
     const float* df = t->dfilm + (size_t)i * 2 * C;
+    if (film_tc) {
+      const int W4 = 4 * C, NF = ntb * 2 * C;
+      if (!stT_ready) {
+        launch_transpose_pad<bf16>(t->st_bf, W4, t->stT, t->Bp, B, t->Bp, W4, nullptr, s);
+        stT_ready = true;
+      }
+      dim3 grid((t->Bp + 31) / 32, (2 * C + 31) / 32), block(32, 8);
+      k_dfilm_prepare<<<grid, block, 0, s>>>(df, NF, t->dfilm_bf + (size_t)i * 2 * C, NF, t->trF + (size_t)i * 2 * C * t->Bp, t->Bp,
+                                             B, 2 * C, G(P.time_blocks[i] + ".mlp.1.bias"));
+      const int tiles = tc_plan_tiles(t->tc_dwf[i], 2 * C), kblocks = t->Bp / 64;
+      int ksplit = std::max(1, std::min(148 / std::max(1, tiles), kblocks));
+      const int kb_per = (kblocks + ksplit - 1) / ksplit;
+      ksplit = (kblocks + kb_per - 1) / kb_per;
+      tc_plan_set_atomic_out(t->tc_dwf[i], G(P.time_blocks[i] + ".mlp.1.weight"), W4, ksplit);
+      launch_gemm_tc(t->tc_dwf[i], 2 * C, s);
+      pending[P.time_blocks[i] + ".mlp.1.weight"] = false;
+      pending[P.time_blocks[i] + ".mlp.1.bias"] = false;
+      return;
+    }
     launch_gemm_tn<float, float>(df, ntb * 2 * C, t->st, 4 * C, G(P.time_blocks[i] + ".mlp.1.weight"), 4 * C, B, 2 * C, 4 * C, s);
     launch_colsum<float>(df, ntb * 2 * C, G(P.time_blocks[i] + ".mlp.1.bias"), B, 2 * C, s);
     launch_gemm_nn<float, float, float>(df, ntb * 2 * C, F(P.time_blocks[i] + ".mlp.1.weight"), 4 * C, t->dst, 4 * C, B, 4 * C,
@@ -640,7 +793,12 @@ static int train_step_t(ds_handle* h, const float* flat, const float* x0, const 
   }
 
   cudaEventRecord(t->ev[4], s);
-  // ---- 5. what is left of the conditioning paths (fp32): the shared time MLP, d(context)
+  // ---- 5. what is left of the conditioning paths: d(SiLU(temb)) from all blocks, the shared time MLP (fp32), d(context)
+  if (film_tc) {
+    int e = launch_gemm_tc(t->tc_dst, t->Bp, s);      // [B, 19 x 2C] x [19 x 2C, 4C], fp32 accumulation over all blocks
+    if (e) return fail(DS_ERR_CUDA, "train: d(time embedding) GEMM failed: %s", cudaGetErrorString((cudaError_t)e));
+    k_bf16_to_f32<<<((int64_t)B * 4 * C + 255) / 256, 256, 0, s>>>(t->dst_bf, 4 * C, t->dst, 4 * C, B, 4 * C);
+  }
   k_mul_actgrad<<<((int64_t)B * 4 * C + 255) / 256, 256, 0, s>>>(t->dst, t->temb, t->dtemb, (int64_t)B * 4 * C, ACT_SILU);
   launch_gemm_tn<float, float>(t->dtemb, 4 * C, t->h1, 4 * C, G("time_mlp.3.weight"), 4 * C, B, 4 * C, 4 * C, s);
   launch_colsum<float>(t->dtemb, 4 * C, G("time_mlp.3.bias"), B, 4 * C, s);
