@@ -58,6 +58,7 @@ struct TcEpi {
   int plain;             // channels-on-lanes kernel without GroupNorm: bias, activation, residual only
   float* d32;            // row-major plain kernel: fp32 output accumulated with atomics (split-K weight-gradient GEMMs)
   int ksplit;            // ... number of K splits (work units = tiles x ksplit)
+  int wide_pass1;        // channels-on-lanes kernel, N = 12: statistics pass reads its 48 TMEM columns with x32 + x16 loads
   int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
 };
@@ -632,9 +633,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 // lanes of a warp to hold the channels in the order 8 (lane % 4) + lane / 4.  The host stores the weight rows of
 // these convs in exactly that order inside every block of 32 (ds_commit_weights), so the shuffle costs nothing.
 // GroupNorm statistics: per-(scene, channel) partials -> shared memory -> 8 threads per (scene, group) reduce.
-template <int NOBJ, bool PAIR = true>
+template <int NOBJ, bool PAIR = true, int SC_ = 0, bool SP = false>
 struct GntCfg {
-  static constexpr int SC = (NOBJ == 12) ? 16 : 256 / NOBJ;   // scenes per tile (16 for N = 12, 12 for N = 21)
+  // scenes per tile: 16 for N = 12 (UMMA N = 192), 12 for N = 21 (252 -> 256); SC_ = 20 selects 240-token tiles for
+  // N = 12 (an N = 192 MMA measures about the cycles of an N = 256 one, so wider tiles use the tensor pipe better)
+  static constexpr int SC = SC_ > 0 ? SC_ : ((NOBJ == 12) ? 16 : 256 / NOBJ);
   static constexpr int TOK = SC * NOBJ;                         // tokens per tile (192 / 252)
   static constexpr int UN = (TOK + 15) / 16 * 16;               // UMMA N = TMA box rows of the activation tile
   static constexpr int EPI_W = 16;                              // epilogue warps: 4 per TMEM lane quadrant
@@ -643,7 +646,10 @@ struct GntCfg {
   static constexpr int THREADS = 64 + EPI_W * 32;
   static constexpr int B_BYTES = UN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (UN <= 192) ? 4 : 3;
+  // SP ("spill") variant: the statistics pass parks the bf16-rounded accumulator of the warp's scenes in shared memory
+  // (lane-contiguous words, no bank conflicts, private to the thread that wrote them) so that the accumulator is read
+  // from TMEM only once and released before the normalisation pass; costs one pipeline stage of shared memory
+  static constexpr int STAGES = (UN <= 192) ? (SP ? 3 : 4) : 3;
   static constexpr int ACC_STRIDE = 256;                        // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 512;
   static constexpr int CHAN_MAX_N = 512;
@@ -665,7 +671,10 @@ struct GntCfg {
   static constexpr int RED_OFF = SCRATCH_OFF + CHAN_BYTES;
   static constexpr int STAT_OFF = RED_OFF + RED_BYTES;
   static constexpr int STG_OFF = (STAT_OFF + STAT_BYTES + 127) / 128 * 128;
-  static constexpr int SMEM_BYTES = 1024 + STG_OFF + EPI_W * 2 * STG_BYTES;
+  static constexpr int SPILL_OFF = STG_OFF + EPI_W * 2 * STG_BYTES;
+  // [warp][scene][pair][lane] words; the warp's last scene stays in registers
+  static constexpr int SPILL_BYTES = SP ? EPI_W * (SPP - 1) * NPAIR * 128 : 0;
+  static constexpr int SMEM_BYTES = 1024 + SPILL_OFF + SPILL_BYTES;
   static_assert(SC % NP == 0, "scenes must split evenly over the warps of a quadrant");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must stay swizzle-atom aligned");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -736,12 +745,14 @@ __device__ __forceinline__ void stsm_x2_t(uint32_t addr, uint32_t r0, uint32_t r
   asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
 }
 
-template <int NOBJ, bool PAIR>
+template <int NOBJ, bool PAIR, int SC_, bool SP>
 // 18 warps = 5 on the fullest SM sub-partition: 16384 / (5 * 32) = 102 registers per thread at most
 __global__ void __maxnreg__(96)
 k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x0,
            const __grid_constant__ CUtensorMap tm_x1, TcEpi epi, int* err_flag) {
-  using Cfg = GntCfg<NOBJ, PAIR>;
+  using Cfg = GntCfg<NOBJ, PAIR, SC_, SP>;
+  static_assert(!PAIR || Cfg::SPP <= 4, "the warp-pair statistics exchange packs at most 4 scenes per warp");
+  static_assert(!SP || (!PAIR && NOBJ % 2 == 0), "the spill variant is written for the default statistics path and even N");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -898,6 +909,9 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     // staging blocks of this warp: [token][32 channels] bf16, 64 B rows
     const uint32_t stg_in = base + uint32_t(Cfg::STG_OFF) + uint32_t((warp - 2) * 2 * Cfg::STG_BYTES);
     const uint32_t stg_out = stg_in + uint32_t(Cfg::STG_BYTES);
+    // spill words of this thread (SP variant only): [scene][pair][lane]
+    uint32_t* const spill = reinterpret_cast<uint32_t*>(base_ptr + Cfg::SPILL_OFF) + (warp - 2) * ((Cfg::SPP - 1) * Cfg::NPAIR * 32) + lane;
+    uint32_t keep[SP ? Cfg::NPAIR : 1];               // packed values of the warp's last scene (SP variant)
     // ldmatrix / stmatrix row address of this lane: matrix lane / 8 holds tokens 2 (lane / 8) + {0, 1}; its row
     // (lane % 8) = 2 * chunk + e is the 16-byte chunk `chunk` (8 channels) of token 2 (lane / 8) + e
     const uint32_t mrow = uint32_t((2 * (lane >> 3) + (lane & 1)) * 64 + ((lane & 7) >> 1) * 16);
@@ -1057,7 +1071,38 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
 
         } else {
         // ---- pass 1: per-(scene, channel) sums of acc and acc^2 over the scene's tokens, bias folded analytically
-        if constexpr (FM != 4) {
+        if constexpr (FM != 4 && NOBJ == 12 && Cfg::SPP == 4 && !SP) {
+          // all four scenes of this warp (48 accumulator columns) with two wide TMEM loads instead of eight narrow ones
+          // (DS_GNT_WIDE1=0 selects the per-scene loads; A/B in profiles/)
+          if (epi.wide_pass1) {
+            uint32_t w32[32], w16[16];
+            tmem_ld32_issue(taddr, w32);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(w16[0]), "=r"(w16[1]), "=r"(w16[2]), "=r"(w16[3]), "=r"(w16[4]), "=r"(w16[5]), "=r"(w16[6]),
+                           "=r"(w16[7]), "=r"(w16[8]), "=r"(w16[9]), "=r"(w16[10]), "=r"(w16[11]), "=r"(w16[12]),
+                           "=r"(w16[13]), "=r"(w16[14]), "=r"(w16[15])
+                         : "r"(taddr + 32u)
+                         : "memory");
+            tmem_ld_wait();
+            float2* rdst = red + s_begin * 128 + 32 * q + lane;
+#pragma unroll
+            for (int si = 0; si < 4; ++si) {
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 12; ++j) {
+                const int col = si * 12 + j;
+                const float v = __uint_as_float(col < 32 ? w32[col < 32 ? col : 0] : w16[col >= 32 ? col - 32 : 0]);
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+              }
+              const float S = fmaf(12.0f, bias, s1);
+              const float SS = fmaf(bias, fmaf(12.0f, bias, 2.0f * s1), s2);
+              rdst[si * 128] = make_float2(S, SS);
+            }
+          }
+        }
+        if (FM != 4 && !(NOBJ == 12 && Cfg::SPP == 4 && !SP && epi.wide_pass1)) {
           uint32_t va[NOBJ];
           tmem_ld_scene_issue(taddr, va);
           float2* rdst = red + s_begin * 128 + 32 * q + lane;
@@ -1077,6 +1122,19 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             const float S = fmaf(float(NOBJ), bias, s1);
             const float SS = fmaf(bias, fmaf(float(NOBJ), bias, 2.0f * s1), s2);
             rdst[si * 128] = make_float2(S, SS);
+            if constexpr (SP) {
+#pragma unroll
+              for (int i = 0; i < Cfg::NPAIR; ++i) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                if (si + 1 < Cfg::SPP) spill[(si * Cfg::NPAIR + i) * 32] = *reinterpret_cast<uint32_t*>(&h2);
+                else keep[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+            }
+          }
+          if constexpr (SP) {      // the accumulator has been read: the next-but-one tile's MMAs may start already
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(ab));
           }
         }
         if constexpr (FM != 4) epi_bar();
@@ -1135,10 +1193,18 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
               b = fmaf(bias - st.x, a, Qs);
             }
           }
-          tmem_ld_scene_wait(va);
           float y[2 * Cfg::PKN];                      // tokens >= NOBJ: padding of the last pair(s), never stored
 #pragma unroll
           for (int j = NOBJ; j < 2 * Cfg::PKN; ++j) y[j] = 0.f;
+          if constexpr (SP && FM != 4) {              // values parked by pass 1; TMEM was released there
+#pragma unroll
+            for (int i = 0; i < Cfg::NPAIR; ++i) {
+              const uint32_t w = si + 1 < Cfg::SPP ? spill[(si * Cfg::NPAIR + i) * 32] : keep[i];
+              y[2 * i] = fmaf(__uint_as_float(w << 16), a, b);
+              y[2 * i + 1] = fmaf(__uint_as_float(w & 0xffff0000u), a, b);
+            }
+          } else {
+          tmem_ld_scene_wait(va);
 #pragma unroll
           for (int j = 0; j < NOBJ; ++j) y[j] = FM == 4 ? __uint_as_float(va[j]) + b : fmaf(__uint_as_float(va[j]), a, b);
           if (si + 1 < Cfg::SPP) tmem_ld_scene_issue(taddr + uint32_t((si + 1) * NOBJ), va);
@@ -1146,6 +1212,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(ab));          // accumulator drained: the next tile's MMAs may start
+          }
           }
           if constexpr (FM == 1) {
             if constexpr (OBJ_IN_REGS) {
@@ -1324,10 +1391,13 @@ bool tc_runtime_available(char* err, int err_len) {
   cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_gnt<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, true>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_gnt<21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, true>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_gnt<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false>::SMEM_BYTES);
-  cudaFuncSetAttribute(k_gemm_gnt<21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<21, true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<21, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, false, 20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false, 20>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       GntCfg<12, false, 0, true>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
   return true;
 }
@@ -1349,6 +1419,12 @@ static bool encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
     return false;
   }
   return true;
+}
+
+// scenes per tile of the channels-on-lanes kernel for N = 12: 16 (default) or 20 (DS_GNT_SC=20, A/B switch)
+static int gnt_scenes_per_tile(int n_obj) {
+  static const int sc = getenv("DS_GNT_SC") ? atoi(getenv("DS_GNT_SC")) : 16;
+  return n_obj == 12 ? (sc == 20 ? 20 : 16) : 12;
 }
 
 TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int err_len) {
@@ -1396,7 +1472,9 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     if (const char* e = getenv("DS_GNT_CLUSTER")) gnt_cs = atoi(e);
     if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
   }
-  const int gnt_un = g.n_obj == 21 ? GntCfg<21, true>::UN : GntCfg<12, true>::UN, gnt_tok = g.n_obj == 21 ? GntCfg<21, true>::TOK : GntCfg<12, true>::TOK;
+  const int gnt_sc20 = gnt_scenes_per_tile(g.n_obj) == 20;
+  const int gnt_un = g.n_obj == 21 ? GntCfg<21, true>::UN : (gnt_sc20 ? GntCfg<12, false, 20>::UN : GntCfg<12, true>::UN);
+  const int gnt_tok = g.n_obj == 21 ? GntCfg<21, true>::TOK : (gnt_sc20 ? GntCfg<12, false, 20>::TOK : GntCfg<12, true>::TOK);
   const uint32_t act_box = gnt ? uint32_t(gnt_un / gnt_cs) : uint32_t(BM);     // rows of one activation load
   bool ok = encode_2d(&p->tm_a0, g.a0, g.k0, rows_capacity, g.lda0, act_box, err, err_len);
   if (ok && g.a1) ok = encode_2d(&p->tm_a1, g.a1, g.k1, rows_capacity, g.lda1, act_box, err, err_len);
@@ -1441,6 +1519,9 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     // measured (profiles/round2_gnt_ab.txt): the prefetch makes the residual variants 4-5 % SLOWER -- off by default
     static const int pf = getenv("DS_GNT_PREFETCH") ? atoi(getenv("DS_GNT_PREFETCH")) : 0;
     p->epi.res_prefetch = pf;
+    // measured (profiles/round2_gnt_ab.txt): no difference (39.1 vs 39.2 us) -> off
+    static const int wide = getenv("DS_GNT_WIDE1") ? atoi(getenv("DS_GNT_WIDE1")) : 0;
+    p->epi.wide_pass1 = wide;
   }
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
@@ -1511,9 +1592,9 @@ static bool gnt_nobj_ok(int n_obj) {
 bool tc_gnt_plain_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0; }
 bool tc_gnt_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0 && N <= GntCfg<12, true>::CHAN_MAX_N; }
 
-template <int NOBJ, bool PAIR>
+template <int NOBJ, bool PAIR, int SC_ = 0, bool SP = false>
 static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cudaStream_t s) {
-  using Cfg = GntCfg<NOBJ, PAIR>;
+  using Cfg = GntCfg<NOBJ, PAIR, SC_, SP>;
   const int n_scenes = epi.M / NOBJ;
   const int cs = p->cluster;
   const int total = ((n_scenes + Cfg::SC - 1) / Cfg::SC) * (epi.N / BM / cs);      // work units per cluster
@@ -1544,14 +1625,14 @@ static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cuda
       cfg.numAttrs = na;
       cfg.gridDim = dim3(max_cl * cs);
       int n = 0;
-      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<NOBJ, PAIR>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
+      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<NOBJ, PAIR, SC_, SP>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
     }
     if (cached < max_cl) max_cl = cached;
   }
   cfg.attrs = na ? attr : nullptr;
   cfg.numAttrs = na;
   cfg.gridDim = dim3((total < max_cl ? total : max_cl) * cs);
-  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<NOBJ, PAIR>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<NOBJ, PAIR, SC_, SP>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
 }
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
@@ -1563,6 +1644,10 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
     // GroupNorm statistics exchange: 0 (default) two CTA-wide barriers, 1 warp-pair local (named 64-thread barriers);
     // A/B on one box (profiles/round2_gnt_ab.txt): no difference (39.3 / 43.2 / 66.3 us vs 40.0 / 43.2 / 66.0 us)
     static const int pair = getenv("DS_GNT_PAIR") ? atoi(getenv("DS_GNT_PAIR")) : 0;
+    if (epi.n_obj == 12 && gnt_scenes_per_tile(12) == 20) return launch_gnt<12, false, 20>(p, epi, fd, s);
+    // DS_GNT_SPILL=1 (A/B switch, N = 12): single TMEM read, normalisation pass from shared memory
+    static const int spill = getenv("DS_GNT_SPILL") ? atoi(getenv("DS_GNT_SPILL")) : 0;
+    if (spill && epi.n_obj == 12) return launch_gnt<12, false, 0, true>(p, epi, fd, s);
     if (pair) return epi.n_obj == 21 ? launch_gnt<21, true>(p, epi, fd, s) : launch_gnt<12, true>(p, epi, fd, s);
     return epi.n_obj == 21 ? launch_gnt<21, false>(p, epi, fd, s) : launch_gnt<12, false>(p, epi, fd, s);
   }

@@ -52,6 +52,27 @@ run_task() {
         bench.py --gpus 2 --config train --steps 5 --warmup 3 2>gpurun_out/${TAG}_dp2_train.err | tail -1 | tee gpurun_out/${TAG}_dp2_train.json
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
         bench.py --gpus 2 --steps 2 --warmup 2 --no-cpu-baseline "$@" 2>gpurun_out/${TAG}_dp2_sample.err | tail -1 | tee gpurun_out/${TAG}_dp2_sample.json ;;
+    probe-wide)    # A/B of the wide TMEM loads in the statistics pass of k_gemm_gnt
+      for w in 0 1 0 1; do
+        echo "== DS_GNT_WIDE1=$w"
+        DS_GNT_WIDE1=$w GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -E "^(GNT|   check GNT)" | grep -E "M=49152|MISMATCH"
+      done | tee gpurun_out/${TAG}_probe_wide.txt ;;
+    probe-sc)      # A/B of the k_gemm_gnt tile width (16 vs 20 scenes) with numeric checks, then a short bench of each
+      for sc in 16 20; do
+        echo "== DS_GNT_SC=$sc"
+        DS_GNT_SC=$sc GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -E "^(GNT|   check GNT|   prod_wait)" | grep -B0 -A1 -E "GNT.*M=49152|check GNT|MISMATCH" | grep -v "^--"
+      done | tee gpurun_out/${TAG}_probe_sc.txt
+      for sc in 16 20; do
+        DS_GNT_SC=$sc timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('SC=$sc', d['value'], d['ms_per_step'], d['clocks'])"
+      done | tee -a gpurun_out/${TAG}_probe_sc.txt ;;
+    probe-spill)   # A/B of the single-TMEM-read epilogue (DS_GNT_SPILL) with numeric checks, then a short bench of each
+      for sp in 0 1; do
+        echo "== DS_GNT_SPILL=$sp"
+        DS_GNT_SPILL=$sp GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -E "^(GNT|   check GNT|   prod_wait)" | grep -B0 -A1 -E "GNT.*M=49152|check GNT|MISMATCH" | grep -v "^--"
+      done | tee gpurun_out/${TAG}_probe_spill.txt
+      for sp in 0 1; do
+        DS_GNT_SPILL=$sp timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('SPILL=$sp', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
+      done | tee -a gpurun_out/${TAG}_probe_spill.txt ;;
     probe-ab)      # A/B of the k_gemm_gnt switches on one box: statistics exchange x residual L2 prefetch
       for pair in 0 1; do for pf in 0 1; do
         echo "== DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf"
