@@ -67,6 +67,7 @@ struct AtEpi {
   bf16* o; int ldo;                 // [M, 128]
   int M, kblocks;
   uint64_t desc_hi;
+  int uni_issue;           // see tc_common.cuh (DS_TC_UNI)
 };
 
 __device__ __forceinline__ float at_exp2(float x) {
@@ -235,7 +236,7 @@ k_ln_qkv_attn(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
   float2* const stat_s = reinterpret_cast<float2*>(base_ptr + AT_STAT_OFF);
   bf16* const stg = reinterpret_cast<bf16*>(base_ptr + AT_STG_OFF);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
@@ -262,25 +263,33 @@ k_ln_qkv_attn(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
   const int kblocks = epi.kblocks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer.  UNI: the whole warp walks the loop, one elected lane issues (see tc_common.cuh)
+    auto producer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = tile * Cfg::ROWS;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 21);
-          mbar_expect_tx(full_bar(stage), AT_STAGE_BYTES);
+          mbar_expect_tx_r<UNI>(full_bar(stage), AT_STAGE_BYTES);
           const uint32_t sa = base + stage * AT_STAGE_BYTES;
-          tma_load_2d(sa, &tm_x, kb * BK, m0, full_bar(stage));
+          tma_load_2d_r<UNI>(sa, &tm_x, kb * BK, m0, full_bar(stage));
 #pragma unroll
           for (int r3 = 0; r3 < 3; ++r3)      // W' slab: three boxes of 128 rows -> [384 rows][128 B]
-            tma_load_2d(sa + A_BYTES + r3 * 128 * BK * 2, &tm_w, kb * BK, r3 * 128, full_bar(stage));
+            tma_load_2d_r<UNI>(sa + A_BYTES + r3 * 128 * BK * 2, &tm_w, kb * BK, r3 * 128, full_bar(stage));
           if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
-    }
+    };
+    if (epi.uni_issue) producer(std::true_type{});
+    else producer(std::false_type{});
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer
+    auto issuer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -296,15 +305,17 @@ k_ln_qkv_attn(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
           const uint64_t b1 = umma_desc(sa + A_BYTES + 256 * BK * 2, epi.desc_hi);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(tmem_base, adesc + uint64_t(2 * k), b0 + uint64_t(2 * k), AT_IDESC_256, (kb | k) != 0);
-            umma_bf16(tmem_base + 256u, adesc + uint64_t(2 * k), b1 + uint64_t(2 * k), AT_IDESC_128, (kb | k) != 0);
+            umma_issue<UNI>(tmem_base, adesc + uint64_t(2 * k), b0 + uint64_t(2 * k), AT_IDESC_256, (kb | k) != 0);
+            umma_issue<UNI>(tmem_base + 256u, adesc + uint64_t(2 * k), b1 + uint64_t(2 * k), AT_IDESC_128, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));
+          umma_arrive<UNI>(empty_bar(stage));
           if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar);
+        umma_arrive<UNI>(tfull_bar);
       }
-    }
+    };
+    if (epi.uni_issue) issuer(std::true_type{});
+    else issuer(std::false_type{});
   } else {
     // ---------------- epilogue / core warps ----------------
     const int ew = warp - 2;                     // 0..15
@@ -458,6 +469,7 @@ AttnQkvPlan* attn_qkv_plan_create(const void* x, int ldx, const void* w, int ldw
   p->epi.ldo = ldo;
   p->epi.kblocks = K / BK;
   p->epi.desc_hi = umma_desc_hi_sw128();
+  p->epi.uni_issue = tc_uniform_issue();
   p->n_obj = n_obj;
   p->num_sms = tc_num_sms();
   return p;

@@ -55,6 +55,7 @@ struct LnEpi {
   const bf16* res; int ldres;      // residual added after the norm, or nullptr
   int M, kblocks;
   uint64_t desc_hi;
+  int uni_issue;           // see tc_common.cuh (DS_TC_UNI)
 };
 
 __global__ void __launch_bounds__(LN_THREADS, 1)
@@ -74,7 +75,7 @@ k_gemm_ln(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
   float* const g_s = bias_s + LN_C;
   float2* const part = reinterpret_cast<float2*>(base_ptr + LN_PART_OFF);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
@@ -101,26 +102,34 @@ k_gemm_ln(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
   const int kblocks = epi.kblocks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer.  UNI: the whole warp walks the loop, one elected lane issues (see tc_common.cuh)
+    auto producer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       // the whole weight matrix, once: per k-block two boxes of 256 rows x 64 columns -> [512 rows][128 B] slabs
-      mbar_expect_tx(wfull_bar, uint32_t(kblocks * LN_C * BK * 2));
+      mbar_expect_tx_r<UNI>(wfull_bar, uint32_t(kblocks * LN_C * BK * 2));
       for (int kb = 0; kb < kblocks; ++kb) {
-        tma_load_2d(base + uint32_t(kb * LN_C * BK * 2), &tm_w, kb * BK, 0, wfull_bar);
-        tma_load_2d(base + uint32_t(kb * LN_C * BK * 2 + 256 * BK * 2), &tm_w, kb * BK, 256, wfull_bar);
+        tma_load_2d_r<UNI>(base + uint32_t(kb * LN_C * BK * 2), &tm_w, kb * BK, 0, wfull_bar);
+        tma_load_2d_r<UNI>(base + uint32_t(kb * LN_C * BK * 2 + 256 * BK * 2), &tm_w, kb * BK, 256, wfull_bar);
       }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 11);
-          mbar_expect_tx(full_bar(stage), A_BYTES);
-          tma_load_2d(base + LN_A_OFF + stage * A_BYTES, &tm_a, kb * BK, tile * BM, full_bar(stage));
+          mbar_expect_tx_r<UNI>(full_bar(stage), A_BYTES);
+          tma_load_2d_r<UNI>(base + LN_A_OFF + stage * A_BYTES, &tm_a, kb * BK, tile * BM, full_bar(stage));
           if (++stage == LN_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
-    }
+    };
+    if (epi.uni_issue) producer(std::true_type{});
+    else producer(std::false_type{});
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer
+    auto issuer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       mbar_wait(wfull_bar, 0, err_flag, 12);
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
@@ -136,15 +145,17 @@ k_gemm_ln(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
           const uint64_t b1 = umma_desc(base + uint32_t(kb * LN_C * BK * 2 + 256 * BK * 2), epi.desc_hi);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(tmem_base, adesc + uint64_t(2 * k), b0 + uint64_t(2 * k), LN_IDESC, (kb | k) != 0);
-            umma_bf16(tmem_base + 256u, adesc + uint64_t(2 * k), b1 + uint64_t(2 * k), LN_IDESC, (kb | k) != 0);
+            umma_issue<UNI>(tmem_base, adesc + uint64_t(2 * k), b0 + uint64_t(2 * k), LN_IDESC, (kb | k) != 0);
+            umma_issue<UNI>(tmem_base + 256u, adesc + uint64_t(2 * k), b1 + uint64_t(2 * k), LN_IDESC, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));
+          umma_arrive<UNI>(empty_bar(stage));
           if (++stage == LN_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar);
+        umma_arrive<UNI>(tfull_bar);
       }
-    }
+    };
+    if (epi.uni_issue) issuer(std::true_type{});
+    else issuer(std::false_type{});
   } else {
     // ---------------- epilogue warps ----------------
     const int q = warp & 3;                        // TMEM lane quadrant
@@ -369,6 +380,7 @@ LnGemmPlan* ln_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->epi.M = g.M;
   p->epi.kblocks = g.k0 / BK;
   p->epi.desc_hi = umma_desc_hi_sw128();
+  p->epi.uni_issue = tc_uniform_issue();
   p->num_sms = tc_num_sms();
   return p;
 }

@@ -59,6 +59,7 @@ struct TcEpi {
   float* d32;            // row-major plain kernel: fp32 output accumulated with atomics (split-K weight-gradient GEMMs)
   int ksplit;            // ... number of K splits (work units = tiles x ksplit)
   int wide_pass1;        // channels-on-lanes kernel, N = 12: statistics pass reads its 48 TMEM columns with x32 + x16 loads
+  int uni_issue;         // producer / MMA warps run their loops warp-uniformly and elect the issuing lane (DS_TC_UNI)
   int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
 };
@@ -124,7 +125,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   uint8_t* const aux = scratch + Cfg::CHAN_BYTES + Cfg::PART_BYTES + 512 + (GN ? Cfg::AB_BYTES : 0);
   uint32_t* const film_o = reinterpret_cast<uint32_t*>(aux);       // [col][obj] packed bf16x2 (scale + 1, shift)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // programmatic dependent launch: let the next kernel's CTAs be scheduled as SMs drain (its prologue overlaps
   // our tail); our own dependent work starts only after griddepcontrol.wait below
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -174,7 +175,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   const int kb_per = (kblocks + ksplit - 1) / ksplit;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer.  UNI: the whole warp walks the loop, one elected lane issues (see tc_common.cuh)
+    auto producer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       int stage = 0;
       uint32_t phase = 0;
       unsigned long long tw = 0, tstart = clock64();
@@ -186,27 +190,32 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           unsigned long long t0 = epi.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          mbar_expect_tx_r<UNI>(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          if (kb < epi.kb0) tma_load_2d(sa, &tm_a0, kb * BK, m0, full_bar(stage));
-          else tma_load_2d(sa, &tm_a1, (kb - epi.kb0) * BK, m0, full_bar(stage));
+          if (kb < epi.kb0) tma_load_2d_r<UNI>(sa, &tm_a0, kb * BK, m0, full_bar(stage));
+          else tma_load_2d_r<UNI>(sa, &tm_a1, (kb - epi.kb0) * BK, m0, full_bar(stage));
           if (cs == 1) {
-            tma_load_2d(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN, full_bar(stage));
+            tma_load_2d_r<UNI>(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN, full_bar(stage));
           } else {
             const int rows = BN / int(cs);      // this CTA's slice of the weight tile, broadcast to the cluster
-            tma_load_2d_mc(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), &tm_w, kb * BK,
-                           n_idx * BN + int(crank) * rows, full_bar(stage), cmask);
+            tma_load_2d_mc_r<UNI>(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), &tm_w, kb * BK,
+                                  n_idx * BN + int(crank) * rows, full_bar(stage), cmask);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
-      if (epi.trace) {
+      if (epi.trace && lane == 0) {
         epi.trace[blockIdx.x * 8 + 0] = tw;
         epi.trace[blockIdx.x * 8 + 1] = clock64() - tstart;
       }
-    }
+    };
+    if (epi.uni_issue) producer(std::true_type{});
+    else producer(std::false_type{});
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer
+    auto issuer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       int stage = 0;
       uint32_t phase = 0;
       int ab = 0;
@@ -230,21 +239,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), epi.idesc, ((kb - kb_lo) | k) != 0);
+            umma_issue<UNI>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), epi.idesc, ((kb - kb_lo) | k) != 0);
           }
-          if (cs == 1) umma_commit(empty_bar(stage));     // smem slot reusable once these MMAs have read it
-          else umma_commit_mc(empty_bar(stage), cmask);   // ... in every CTA of the cluster
+          if (cs == 1) umma_arrive<UNI>(empty_bar(stage));     // smem slot reusable once these MMAs have read it
+          else umma_arrive_mc<UNI>(empty_bar(stage), cmask);   // ... in every CTA of the cluster
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(ab));               // accumulator complete -> epilogue
+        umma_arrive<UNI>(tfull_bar(ab));               // accumulator complete -> epilogue
         if (++ab == 2) { ab = 0; aphase ^= 1u; }
       }
-      if (epi.trace) {
+      if (epi.trace && lane == 0) {
         epi.trace[blockIdx.x * 8 + 2] = tw_te;
         epi.trace[blockIdx.x * 8 + 3] = tw_f;
         epi.trace[blockIdx.x * 8 + 4] = clock64() - tstart;
       }
-    }
+    };
+    if (epi.uni_issue) issuer(std::true_type{});
+    else issuer(std::false_type{});
   } else {
     // ---------------- epilogue warps ----------------
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
@@ -772,7 +783,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   float2* const red = reinterpret_cast<float2*>(base_ptr + Cfg::RED_OFF);        // !PAIR layout
   float2* const stat = reinterpret_cast<float2*>(base_ptr + Cfg::STAT_OFF);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // Optional thread-block cluster (DS_GNT_CLUSTER=2): the CS CTAs of a cluster work on CS channel tiles of the SAME
   // token tile and share the activation tile -- each CTA loads 1 / CS of its rows and multicasts the slice into every
@@ -819,7 +830,10 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   const int kblocks = epi.kb0 + epi.kb1;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer.  UNI: the whole warp walks the loop, one elected lane issues (see tc_common.cuh)
+    auto producer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       int stage = 0;
       uint32_t phase = 0;
       unsigned long long tw = 0, tstart = clock64();
@@ -830,28 +844,33 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           unsigned long long t0 = epi.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          mbar_expect_tx_r<UNI>(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
+          tma_load_2d_r<UNI>(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
           const CUtensorMap* tmx = kb < epi.kb0 ? &tm_x0 : &tm_x1;
           const int kx = (kb < epi.kb0 ? kb : kb - epi.kb0) * BK;
           if (cs == 1) {
-            tma_load_2d(sa + A_BYTES, tmx, kx, m0, full_bar(stage));
+            tma_load_2d_r<UNI>(sa + A_BYTES, tmx, kx, m0, full_bar(stage));
           } else {
             const int rows = Cfg::UN / int(cs);      // this CTA's slice of the activation tile, broadcast to the cluster
-            tma_load_2d_mc(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), tmx, kx, m0 + int(crank) * rows,
-                           full_bar(stage), cmask);
+            tma_load_2d_mc_r<UNI>(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), tmx, kx, m0 + int(crank) * rows,
+                                  full_bar(stage), cmask);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
-      if (epi.trace) {
+      if (epi.trace && lane == 0) {
         epi.trace[blockIdx.x * 8 + 0] = tw;
         epi.trace[blockIdx.x * 8 + 1] = clock64() - tstart;
       }
-    }
+    };
+    if (epi.uni_issue) producer(std::true_type{});
+    else producer(std::false_type{});
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer
+    auto issuer = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      if (!UNI && lane != 0) return;
       int stage = 0;
       uint32_t phase = 0;
       int ab = 0;
@@ -873,20 +892,22 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           const uint64_t bdesc = umma_desc(sa + A_BYTES, epi.desc_hi);      // activations: the N operand
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, (kb | k) != 0);
-          if (cs == 1) umma_commit(empty_bar(stage));     // smem slot reusable once these MMAs have read it
-          else umma_commit_mc(empty_bar(stage), cmask);   // ... in every CTA of the cluster
+            umma_issue<UNI>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, (kb | k) != 0);
+          if (cs == 1) umma_arrive<UNI>(empty_bar(stage));     // smem slot reusable once these MMAs have read it
+          else umma_arrive_mc<UNI>(empty_bar(stage), cmask);   // ... in every CTA of the cluster
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(ab));
+        umma_arrive<UNI>(tfull_bar(ab));
         if (++ab == 2) { ab = 0; aphase ^= 1u; }
       }
-      if (epi.trace) {
+      if (epi.trace && lane == 0) {
         epi.trace[blockIdx.x * 8 + 2] = tw_te;
         epi.trace[blockIdx.x * 8 + 3] = tw_f;
         epi.trace[blockIdx.x * 8 + 4] = clock64() - tstart;
       }
-    }
+    };
+    if (epi.uni_issue) issuer(std::true_type{});
+    else issuer(std::false_type{});
   } else {
     // ---------------- epilogue warps ----------------
     auto epi_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_W * 32) : "memory"); };
@@ -1522,6 +1543,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     // measured (profiles/round2_gnt_ab.txt): no difference (39.1 vs 39.2 us) -> off
     static const int wide = getenv("DS_GNT_WIDE1") ? atoi(getenv("DS_GNT_WIDE1")) : 0;
     p->epi.wide_pass1 = wide;
+    p->epi.uni_issue = tc_uniform_issue();
   }
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);

@@ -5,6 +5,9 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace ds {
@@ -128,6 +131,102 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
       ::"r"(bar), "h"(cta_mask)
       : "memory");
 }
+// ---- warp-uniform issue (UNI = true) ----------------------------------------------------------------------------
+// The single-thread roles (TMA producer, MMA issuer) can run their loops with the WHOLE warp active: control flow is
+// then warp-uniform, descriptors / barrier addresses / loop counters live in uniform registers, and one elected lane
+// executes each tcgen05 / TMA instruction.  Inside an `if (lane == 0)` region the compiler cannot prove that a single
+// thread is active and wraps every UTCHMMA / UTCBAR / UTMALDG in an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY waterfall
+// (19 SASS instructions per MMA on the issuing thread; 4 MMAs + commit back to back in the uniform form).  The warp
+// index must be taken through uniform_warp_idx() for this.  elect.sync picks the same lane for the same member mask
+// every time, so the commits track that lane's MMAs.  UNI = false keeps the lane-0 form (A/B switch DS_TC_UNI).
+// host side: the A/B switch shared by every tcgen05 kernel of the library (default: uniform issue)
+inline int tc_uniform_issue() {
+  static const int v = getenv("DS_TC_UNI") ? atoi(getenv("DS_TC_UNI")) : 1;
+  return v;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0); }
+
+template <bool UNI>
+__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if constexpr (UNI) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  }
+}
+template <bool UNI>
+__device__ __forceinline__ void umma_arrive(uint32_t bar) {
+  if constexpr (UNI) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+template <bool UNI>
+__device__ __forceinline__ void umma_arrive_mc(uint32_t bar, uint16_t cta_mask) {
+  if constexpr (UNI) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar), "h"(cta_mask)
+        : "memory");
+  } else {
+    umma_commit_mc(bar, cta_mask);
+  }
+}
+template <bool UNI>
+__device__ __forceinline__ void mbar_expect_tx_r(uint32_t bar, uint32_t bytes) {
+  if constexpr (UNI) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+        : "memory");
+  } else {
+    mbar_expect_tx(bar, bytes);
+  }
+}
+template <bool UNI>
+__device__ __forceinline__ void tma_load_2d_r(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  if constexpr (UNI) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+  } else {
+    tma_load_2d(dst, map, c0, c1, bar);
+  }
+}
+template <bool UNI>
+__device__ __forceinline__ void tma_load_2d_mc_r(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                                 uint16_t cta_mask) {
+  if constexpr (UNI) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%2, %3}], [%4], %5;\n\t}"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
+        : "memory");
+  } else {
+    tma_load_2d_mc(dst, map, c0, c1, bar, cta_mask);
+  }
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

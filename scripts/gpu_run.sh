@@ -78,6 +78,14 @@ run_task() {
         echo "== DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf"
         DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -E "^(GNT|T qkv|T to_out|T enc.l1)" | grep "M=49152"
       done; done | tee gpurun_out/${TAG}_probe_ab.txt ;;
+    probe-uni)     # A/B of the warp-uniform producer / MMA issue (DS_TC_UNI) with numeric checks, then short benches
+      for u in 0 1; do
+        echo "== DS_TC_UNI=$u"
+        DS_TC_UNI=$u GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "M=49152|MISMATCH|FAILED" | grep -v "^--"
+      done | tee gpurun_out/${TAG}_probe_uni.txt
+      for cfg in "DS_TC_UNI=0" "DS_TC_UNI=1" "DS_TC_UNI=1 DS_GNT_SC=20" "DS_TC_UNI=1 DS_GNT_SPILL=1" "DS_TC_UNI=1 DS_GNT_CLUSTER=2" "DS_TC_UNI=1 DS_TC_PDL=1"; do
+        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
+      done | tee -a gpurun_out/${TAG}_probe_uni.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
