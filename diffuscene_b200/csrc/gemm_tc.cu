@@ -59,6 +59,7 @@ struct TcEpi {
   float* d32;            // row-major plain kernel: fp32 output accumulated with atomics (split-K weight-gradient GEMMs)
   int ksplit;            // ... number of K splits (work units = tiles x ksplit)
   int wide_pass1;        // channels-on-lanes kernel, N = 12: statistics pass reads its 48 TMEM columns with x32 + x16 loads
+  int two_cta;           // channels-on-lanes kernel, cluster of 2: cta_group::2 MMAs (1; 3 = token halves swapped) (DS_GNT_2CTA)
   int uni_issue;         // producer / MMA warps run their loops warp-uniformly and elect the issuing lane (DS_TC_UNI)
   int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
@@ -694,6 +695,12 @@ struct GntCfg {
   static_assert(UN <= 256 && 2 * UN <= TMEM_COLS + (ACC_STRIDE - UN), "accumulators must fit TMEM");
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(UN >> 3) << 17) |
                                     (uint32_t(BM >> 4) << 24);
+  // CTA pair (cta_group::2): M = 256 = the two CTAs' channel tiles, N = the whole token tile (half of its rows in each
+  // CTA's shared memory)
+  static constexpr uint32_t IDESC_2SM = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(UN >> 3) << 17) |
+                                        (uint32_t((2 * BM) >> 4) << 24);
+  static constexpr int STAGE_TX_2SM = 2 * (A_BYTES + B_BYTES / 2);    // bytes both CTAs land per stage (leader's barrier)
+  static_assert(UN % 16 == 0, "each CTA of a pair holds UN / 2 rows of the token tile (whole 8-row swizzle atoms)");
 };
 
 __device__ __forceinline__ void tmem_ld12_issue(uint32_t taddr, uint32_t (&r)[12]) {
@@ -791,26 +798,42 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   const uint32_t cs = cluster_nctarank();
   const uint32_t crank = cluster_ctarank();
   const uint16_t cmask = uint16_t((1u << cs) - 1u);
+  // CTA-pair mode (DS_GNT_2CTA=1, cluster of 2): ONE tcgen05.mma.cta_group::2 of M = 256 covers both CTAs' channel tiles
+  // of the same token tile.  Each CTA loads its own weight tile and HALF of the token tile (224 KB instead of 320 KB
+  // from L2 per tile pair-half, and the tensor core reads 7 KB instead of 10 KB of shared memory per MMA and SM); the
+  // even CTA issues the MMAs for the pair, and every pipeline barrier that gates them lives in that CTA:
+  //   full[s]    leader only: 1 arrival (its own producer, expect_tx = both CTAs' bytes); the peer's TMA completes on it
+  //   empty[s]   both CTAs: 1 arrival each from the leader's multicast commit
+  //   tfull[b]   both CTAs: 1 arrival each from the leader's multicast commit
+  //   tempty[b]  leader only: 2 x 16 arrivals (the epilogue warps of both CTAs)
+  const bool two = epi.two_cta != 0 && cs == 2;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x0);
     tma_prefetch_desc(&tm_x1);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), cs);       // every CTA of the cluster must have consumed the slot
+      mbar_init(empty_bar(s), two ? 1 : cs);       // multicast mode: every CTA of the cluster must have consumed the slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), Cfg::EPI_W);
+      mbar_init(tempty_bar(b), two ? 2 * Cfg::EPI_W : Cfg::EPI_W);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "n"(Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (two) {       // collective over the pair: warp 1 of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -844,11 +867,21 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           unsigned long long t0 = epi.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
-          mbar_expect_tx_r<UNI>(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d_r<UNI>(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
           const CUtensorMap* tmx = kb < epi.kb0 ? &tm_x0 : &tm_x1;
           const int kx = (kb < epi.kb0 ? kb : kb - epi.kb0) * BK;
+          if constexpr (UNI) {
+            if (two) {      // CTA pair: own weight tile + own half of the token tile, bytes counted on the leader's barrier
+              if (crank == 0) mbar_expect_tx_r<true>(full_bar(stage), Cfg::STAGE_TX_2SM);
+              tma_load_2d_2sm_elect(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
+              tma_load_2d_2sm_elect(sa + A_BYTES, tmx, kx, m0 + int(crank ^ uint32_t(epi.two_cta >> 1)) * (Cfg::UN / 2),
+                                    full_bar(stage));
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+          }
+          mbar_expect_tx_r<UNI>(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_2d_r<UNI>(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
           if (cs == 1) {
             tma_load_2d_r<UNI>(sa + A_BYTES, tmx, kx, m0, full_bar(stage));
           } else {
@@ -871,6 +904,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     auto issuer = [&](auto uni_tag) {
       constexpr bool UNI = decltype(uni_tag)::value;
       if (!UNI && lane != 0) return;
+      if (two && crank != 0) return;                 // CTA pair: the even CTA issues for both
       int stage = 0;
       uint32_t phase = 0;
       int ab = 0;
@@ -890,6 +924,16 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = umma_desc(sa, epi.desc_hi);                // weights: the M operand
           const uint64_t bdesc = umma_desc(sa + A_BYTES, epi.desc_hi);      // activations: the N operand
+          if constexpr (UNI) {
+            if (two) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_issue_2sm_elect(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC_2SM, (kb | k) != 0);
+              umma_arrive_2sm_mc_elect(empty_bar(stage), 3);     // the slot is free in BOTH CTAs
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+          }
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_issue<UNI>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, (kb | k) != 0);
@@ -897,7 +941,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           else umma_arrive_mc<UNI>(empty_bar(stage), cmask);   // ... in every CTA of the cluster
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_arrive<UNI>(tfull_bar(ab));
+        if (UNI && two) umma_arrive_2sm_mc_elect(tfull_bar(ab), 3);     // both CTAs' halves of the accumulator are complete
+        else umma_arrive<UNI>(tfull_bar(ab));
         if (++ab == 2) { ab = 0; aphase ^= 1u; }
       }
       if (epi.trace && lane == 0) {
@@ -1155,7 +1200,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           if constexpr (SP) {      // the accumulator has been read: the next-but-one tile's MMAs may start already
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(ab));
+            if (lane == 0) { if (two) mbar_arrive_leader(tempty_bar(ab)); else mbar_arrive(tempty_bar(ab)); }
           }
         }
         if constexpr (FM != 4) epi_bar();
@@ -1232,7 +1277,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           else {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(ab));          // accumulator drained: the next tile's MMAs may start
+            // accumulator drained: the next tile's MMAs may start (CTA pair: counted on the leader's barrier)
+            if (lane == 0) { if (two) mbar_arrive_leader(tempty_bar(ab)); else mbar_arrive(tempty_bar(ab)); }
           }
           }
           if constexpr (FM == 1) {
@@ -1361,14 +1407,15 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   if (cs > 1) cluster_sync_all();        // no CTA leaves while peers may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
-                 : "memory");
+    if (two) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
+static int gnt_two_cta();
 struct TcGemmPlan {
   CUtensorMap tm_a0, tm_a1, tm_w;
   TcEpi epi;
@@ -1491,6 +1538,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   int gnt_cs = 1;
   if (gnt) {
     if (const char* e = getenv("DS_GNT_CLUSTER")) gnt_cs = atoi(e);
+    if (gnt_two_cta()) gnt_cs = 2;                 // CTA-pair MMAs need the cluster of 2
     if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
   }
   const int gnt_sc20 = gnt_scenes_per_tile(g.n_obj) == 20;
@@ -1544,6 +1592,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     static const int wide = getenv("DS_GNT_WIDE1") ? atoi(getenv("DS_GNT_WIDE1")) : 0;
     p->epi.wide_pass1 = wide;
     p->epi.uni_issue = tc_uniform_issue();
+    p->epi.two_cta = (gnt && gnt_cs == 2 && p->epi.uni_issue) ? gnt_two_cta() : 0;
   }
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
@@ -1613,6 +1662,12 @@ static bool gnt_nobj_ok(int n_obj) {
 }
 bool tc_gnt_plain_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0; }
 bool tc_gnt_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0 && N <= GntCfg<12, true>::CHAN_MAX_N; }
+
+// DS_GNT_2CTA: 0 off, 1 cta_group::2 MMAs over a cluster of 2 (3: token-tile halves swapped -- bring-up aid)
+static int gnt_two_cta() {
+  static const int v = getenv("DS_GNT_2CTA") ? atoi(getenv("DS_GNT_2CTA")) : 0;
+  return v;
+}
 
 template <int NOBJ, bool PAIR, int SC_ = 0, bool SP = false>
 static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cudaStream_t s) {

@@ -227,6 +227,46 @@ __device__ __forceinline__ void tma_load_2d_mc_r(uint32_t dst, const CUtensorMap
   }
 }
 
+// ---- CTA pair (cta_group::2): one UMMA of M = 256 spans the two SMs of a cluster of 2 ------------------------------
+// Each CTA keeps its own 128 rows of the M operand and HALF of the N operand's rows in its own shared memory (same
+// offsets in both CTAs); the even ("leader") CTA issues the MMAs for the pair, each CTA's TMEM receives its 128 rows of
+// D.  A shared::cta address used in the shared::cluster window carries the CTA's rank in bit 24, so clearing that bit
+// addresses the leader's copy of a barrier (the convention of the TMA / commit instructions with .cta_group::2).
+static constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+// TMA load into THIS CTA's shared memory whose transaction bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm_elect(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];\n\t}"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & PEER_BIT_MASK)
+      : "memory");
+}
+__device__ __forceinline__ void umma_issue_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of the pair's MMAs -> one arrival on the barrier at this offset in EVERY CTA of the mask
+__device__ __forceinline__ void umma_arrive_2sm_mc_elect(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+// arrive on the LEADER's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

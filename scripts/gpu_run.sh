@@ -86,6 +86,14 @@ run_task() {
       for cfg in "DS_TC_UNI=0" "DS_TC_UNI=1" "DS_TC_UNI=1 DS_GNT_SC=20" "DS_TC_UNI=1 DS_GNT_SPILL=1" "DS_TC_UNI=1 DS_GNT_CLUSTER=2" "DS_TC_UNI=1 DS_TC_PDL=1"; do
         env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
       done | tee -a gpurun_out/${TAG}_probe_uni.txt ;;
+    probe-2cta)    # bring-up of the cta_group::2 mode of k_gemm_gnt: numeric checks + timings, then short benches
+      for v in 0 1 3; do
+        echo "== DS_GNT_2CTA=$v"
+        DS_GNT_2CTA=$v GNT_ONLY=1 GNT_CHECKS=1 timeout 200 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "^GNT|check GNT|MISMATCH|FAILED|rror" | grep -v "^--" | cut -c1-200
+      done | tee gpurun_out/${TAG}_probe_2cta.txt
+      for cfg in "DS_GNT_2CTA=0" "DS_GNT_2CTA=1" "DS_GNT_2CTA=3"; do
+        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
+      done 2>&1 | tee -a gpurun_out/${TAG}_probe_2cta.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
