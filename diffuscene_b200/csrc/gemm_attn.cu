@@ -237,6 +237,7 @@ k_ln_qkv_attn(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
   bf16* const stg = reinterpret_cast<bf16*>(base_ptr + AT_STG_OFF);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // PDL: the next kernel's prologue may overlap our tail
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
@@ -257,6 +258,7 @@ k_ln_qkv_attn(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // nothing above touched memory written by earlier kernels
 
   const int n_scenes = epi.M / NOBJ;
   const int num_tiles = (n_scenes + Cfg::SPT - 1) / Cfg::SPT;
@@ -484,9 +486,10 @@ int launch_ln_qkv_attn(const AttnQkvPlan* p, int M, cudaStream_t s) {
   const int tiles = (n_scenes + spt - 1) / spt;
   if (tiles == 0) return 0;
   const int grid = tiles < p->num_sms ? tiles : p->num_sms;
-  if (p->n_obj == 21) k_ln_qkv_attn<21><<<grid, AT_THREADS, AtCfg<21>::SMEM, s>>>(p->tm_x, p->tm_w, epi, tc_error_flag_dev());
-  else k_ln_qkv_attn<12><<<grid, AT_THREADS, AtCfg<12>::SMEM, s>>>(p->tm_x, p->tm_w, epi, tc_error_flag_dev());
-  return (int)cudaGetLastError();
+  const bool pdl = tc_pdl_enabled(M);
+  if (p->n_obj == 21)
+    return tc_launch(k_ln_qkv_attn<21>, grid, AT_THREADS, AtCfg<21>::SMEM, s, pdl, p->tm_x, p->tm_w, epi, tc_error_flag_dev());
+  return tc_launch(k_ln_qkv_attn<12>, grid, AT_THREADS, AtCfg<12>::SMEM, s, pdl, p->tm_x, p->tm_w, epi, tc_error_flag_dev());
 }
 
 }  // namespace ds

@@ -76,6 +76,7 @@ k_gemm_ln(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
   float2* const part = reinterpret_cast<float2*>(base_ptr + LN_PART_OFF);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // PDL: the next kernel's prologue may overlap our tail
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
@@ -97,6 +98,7 @@ k_gemm_ln(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // nothing above touched memory written by earlier kernels
 
   const int num_tiles = (epi.M + BM - 1) / BM;
   const int kblocks = epi.kblocks;
@@ -392,8 +394,7 @@ int launch_gemm_ln(const LnGemmPlan* p, int M, cudaStream_t s) {
   const int tiles = (M + BM - 1) / BM;
   if (tiles == 0) return 0;
   const int grid = tiles < p->num_sms ? tiles : p->num_sms;
-  k_gemm_ln<<<grid, LN_THREADS, LN_SMEM, s>>>(p->tm_a, p->tm_w, epi, tc_error_flag_dev());
-  return (int)cudaGetLastError();
+  return tc_launch(k_gemm_ln, grid, LN_THREADS, LN_SMEM, s, tc_pdl_enabled(M), p->tm_a, p->tm_w, epi, tc_error_flag_dev());
 }
 
 }  // namespace ds

@@ -59,7 +59,7 @@ struct TcEpi {
   float* d32;            // row-major plain kernel: fp32 output accumulated with atomics (split-K weight-gradient GEMMs)
   int ksplit;            // ... number of K splits (work units = tiles x ksplit)
   int wide_pass1;        // channels-on-lanes kernel, N = 12: statistics pass reads its 48 TMEM columns with x32 + x16 loads
-  int two_cta;           // channels-on-lanes kernel, cluster of 2: cta_group::2 MMAs (1; 3 = token halves swapped) (DS_GNT_2CTA)
+  int two_cta;           // channels-on-lanes kernel, cluster of 2: cta_group::2 MMAs (bit 0 on, bit 1 token halves swapped, bit 2 shallow ring) (DS_GNT_2CTA)
   int uni_issue;         // producer / MMA warps run their loops warp-uniformly and elect the issuing lane (DS_TC_UNI)
   int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
@@ -699,7 +699,12 @@ struct GntCfg {
   // CTA's shared memory)
   static constexpr uint32_t IDESC_2SM = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(UN >> 3) << 17) |
                                         (uint32_t((2 * BM) >> 4) << 24);
-  static constexpr int STAGE_TX_2SM = 2 * (A_BYTES + B_BYTES / 2);    // bytes both CTAs land per stage (leader's barrier)
+  static constexpr int STAGE_BYTES_2SM = A_BYTES + B_BYTES / 2;       // per CTA of a pair
+  static constexpr int STAGE_TX_2SM = 2 * STAGE_BYTES_2SM;            // bytes both CTAs land per stage (leader's barrier)
+  static constexpr int STAGES_2SM = (STAGES * STAGE_BYTES) / STAGE_BYTES_2SM < 6 ? (STAGES * STAGE_BYTES) / STAGE_BYTES_2SM : 6;
+  static constexpr int MAX_STAGES = 6;                                // barrier slots reserved (256 bytes behind the ring)
+  static_assert(STAGE_BYTES_2SM % 1024 == 0, "pair stages must stay swizzle-atom aligned");
+  static_assert(8 * (2 * MAX_STAGES + 5) <= 256, "barrier block");
   static_assert(UN % 16 == 0, "each CTA of a pair holds UN / 2 rows of the token tile (whole 8-row swizzle atoms)");
 };
 
@@ -776,10 +781,10 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::MAX_STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   float* const bias_s = reinterpret_cast<float*>(base_ptr + Cfg::SCRATCH_OFF);
   float2* const gb_s = reinterpret_cast<float2*>(base_ptr + Cfg::SCRATCH_OFF + Cfg::CHAN_MAX_N * 4);
@@ -807,11 +812,16 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   //   tfull[b]   both CTAs: 1 arrival each from the leader's multicast commit
   //   tempty[b]  leader only: 2 x 16 arrivals (the epilogue warps of both CTAs)
   const bool two = epi.two_cta != 0 && cs == 2;
+  // operand ring geometry: the CTA pair stages only half of the token tile per CTA, so the same shared memory holds
+  // more (smaller) stages
+  const bool deep = two && !(epi.two_cta & 4);         // DS_GNT_2CTA |= 4: keep the single-CTA ring geometry (A/B)
+  const int nst = deep ? Cfg::STAGES_2SM : Cfg::STAGES;
+  const uint32_t stb = deep ? uint32_t(Cfg::STAGE_BYTES_2SM) : uint32_t(Cfg::STAGE_BYTES);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x0);
     tma_prefetch_desc(&tm_x1);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < Cfg::MAX_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), two ? 1 : cs);       // multicast mode: every CTA of the cluster must have consumed the slot
     }
@@ -867,16 +877,16 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           unsigned long long t0 = epi.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
-          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sa = base + stage * stb;
           const CUtensorMap* tmx = kb < epi.kb0 ? &tm_x0 : &tm_x1;
           const int kx = (kb < epi.kb0 ? kb : kb - epi.kb0) * BK;
           if constexpr (UNI) {
             if (two) {      // CTA pair: own weight tile + own half of the token tile, bytes counted on the leader's barrier
               if (crank == 0) mbar_expect_tx_r<true>(full_bar(stage), Cfg::STAGE_TX_2SM);
               tma_load_2d_2sm_elect(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
-              tma_load_2d_2sm_elect(sa + A_BYTES, tmx, kx, m0 + int(crank ^ uint32_t(epi.two_cta >> 1)) * (Cfg::UN / 2),
+              tma_load_2d_2sm_elect(sa + A_BYTES, tmx, kx, m0 + int(crank ^ uint32_t((epi.two_cta >> 1) & 1)) * (Cfg::UN / 2),
                                     full_bar(stage));
-              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == nst) { stage = 0; phase ^= 1u; }
               continue;
             }
           }
@@ -889,7 +899,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             tma_load_2d_mc_r<UNI>(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), tmx, kx, m0 + int(crank) * rows,
                                   full_bar(stage), cmask);
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
       }
       if (epi.trace && lane == 0) {
@@ -921,7 +931,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           mbar_wait(full_bar(stage), phase, err_flag, 3);
           if (epi.trace) tw_f += clock64() - t0;
           tc_fence_after();
-          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sa = base + stage * stb;
           const uint64_t adesc = umma_desc(sa, epi.desc_hi);                // weights: the M operand
           const uint64_t bdesc = umma_desc(sa + A_BYTES, epi.desc_hi);      // activations: the N operand
           if constexpr (UNI) {
@@ -930,7 +940,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
               for (int k = 0; k < BK / 16; ++k)
                 umma_issue_2sm_elect(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC_2SM, (kb | k) != 0);
               umma_arrive_2sm_mc_elect(empty_bar(stage), 3);     // the slot is free in BOTH CTAs
-              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == nst) { stage = 0; phase ^= 1u; }
               continue;
             }
           }
@@ -939,7 +949,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             umma_issue<UNI>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC, (kb | k) != 0);
           if (cs == 1) umma_arrive<UNI>(empty_bar(stage));     // smem slot reusable once these MMAs have read it
           else umma_arrive_mc<UNI>(empty_bar(stage), cmask);   // ... in every CTA of the cluster
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
         if (UNI && two) umma_arrive_2sm_mc_elect(tfull_bar(ab), 3);     // both CTAs' halves of the accumulator are complete
         else umma_arrive<UNI>(tfull_bar(ab));
@@ -1630,10 +1640,9 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int pdl = -1;
-  // off by default: with the 576-thread channels-on-lanes kernels in the step program PDL measured 1.5 % SLOWER
-  // (the chip is power-capped; early-resident CTAs polling their barriers cost clock); DS_TC_PDL=1 enables
-  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 0; }
+  // off by default at the throughput batch: with the 576-thread channels-on-lanes kernels in the step program PDL
+  // measured 1.5 % SLOWER (the chip is power-capped; early-resident CTAs polling their barriers cost clock)
+  const bool pdl = tc_pdl_enabled(epi.M);
   if (pdl) {      // may start while the previous kernel in the stream drains (it waits at griddepcontrol.wait)
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
@@ -1682,8 +1691,7 @@ static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cuda
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("DS_TC_PDL"); pdl = e ? atoi(e) : 0; }
+  const bool pdl = tc_pdl_enabled(epi.M);
   if (pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;

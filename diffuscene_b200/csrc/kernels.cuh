@@ -124,6 +124,11 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
 void tc_plan_destroy(TcGemmPlan* p);
 void tc_plan_set_film(TcGemmPlan* p, const FilmRef& f);
 void tc_plan_set_trace(TcGemmPlan* p, unsigned long long* trace);
+// Programmatic-dependent-launch policy shared by every launcher of the library (pointwise.cu).  kind 0: tcgen05 GEMM
+// kernels (DS_TC_PDL), kind 1: pointwise kernels (DS_PW_PDL); values 0 off, 1 on, 2 automatic: on when `rows` (tokens of
+// the launch) <= DS_PDL_ROWS (default 16384) -- the latency / strong-scaling regime, where the kernel prologue is a
+// large share of every launch; at the throughput batch PDL measured 1.5 % slower (profiles/README.md, v9).
+bool pdl_enabled(int kind, int64_t rows);
 void tc_plan_set_atomic_out(TcGemmPlan* p, float* d32, int ldd, int ksplit);      // split-K, fp32 atomics (dW GEMMs)
 int tc_plan_tiles(const TcGemmPlan* p, int M);
 void tc_plan_set_residual(TcGemmPlan* p, const void* res);      // nullptr: plain store; == output: accumulate in place

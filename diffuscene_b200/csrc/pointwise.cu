@@ -12,15 +12,24 @@
 
 namespace ds {
 
+static constexpr int PDL_DEFAULT_MODE = 0;      // 0 off / 1 on / 2 automatic by launch size (see kernels.cuh)
+
 // Programmatic dependent launch for the pointwise kernels of the step program: launched with the PDL attribute, a
 // kernel may be scheduled while the previous kernel in the stream (a GEMM that issued griddepcontrol.launch_dependents)
 // drains; it touches no memory before `pdl_wait()`.  These kernels do NOT trigger their own dependents early (their
 // dependents are 96-register, 216 KB GEMM CTAs that would crowd out the remaining waves).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled(int kind, int64_t rows) {
+  static const int mode[2] = {getenv("DS_TC_PDL") ? atoi(getenv("DS_TC_PDL")) : PDL_DEFAULT_MODE,
+                              getenv("DS_PW_PDL") ? atoi(getenv("DS_PW_PDL")) : PDL_DEFAULT_MODE};
+  static const int64_t auto_rows = getenv("DS_PDL_ROWS") ? atoll(getenv("DS_PDL_ROWS")) : 16384;
+  const int m = mode[kind != 0];
+  return m == 2 ? rows <= auto_rows : m != 0;
+}
+// rows: tokens the launch works on (the automatic policy keys on it); the pointwise kernels pass their row count
 template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
-  static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("DS_PW_PDL"); pdl = e ? atoi(e) : 0; }     // off by default (see gemm_tc.cu)
+static void launch_pdl_rows(int64_t rows, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  const bool pdl = pdl_enabled(1, rows);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -34,6 +43,11 @@ static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.numAttrs = 1;
   }
   (void)cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);   // errors surface at the caller's sync / cudaGetLastError
+}
+// every kernel launched through here uses at least one thread per 4 tokens ... the grid is a good proxy for the rows
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  launch_pdl_rows(int64_t(grid.x) * 8, kern, grid, block, smem, s, std::forward<Args>(args)...);
 }
 
 

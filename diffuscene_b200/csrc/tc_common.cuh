@@ -144,6 +144,24 @@ inline int tc_uniform_issue() {
   static const int v = getenv("DS_TC_UNI") ? atoi(getenv("DS_TC_UNI")) : 1;
   return v;
 }
+inline bool tc_pdl_enabled(int rows) { return pdl_enabled(0, rows); }      // policy: kernels.cuh
+// launch with the optional programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+inline int tc_launch(void (*kern)(KArgs...), int grid, int threads, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return (int)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0); }
 
 template <bool UNI>

@@ -87,13 +87,19 @@ run_task() {
         env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
       done | tee -a gpurun_out/${TAG}_probe_uni.txt ;;
     probe-2cta)    # bring-up of the cta_group::2 mode of k_gemm_gnt: numeric checks + timings, then short benches
-      for v in 0 1 3; do
+      for v in 0 1 3 5; do
         echo "== DS_GNT_2CTA=$v"
         DS_GNT_2CTA=$v GNT_ONLY=1 GNT_CHECKS=1 timeout 200 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "^GNT|check GNT|MISMATCH|FAILED|rror" | grep -v "^--" | cut -c1-200
       done | tee gpurun_out/${TAG}_probe_2cta.txt
-      for cfg in "DS_GNT_2CTA=0" "DS_GNT_2CTA=1" "DS_GNT_2CTA=3"; do
+      for cfg in "DS_GNT_2CTA=0" "DS_GNT_2CTA=1" "DS_GNT_2CTA=3" "DS_GNT_2CTA=5"; do
         env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
       done 2>&1 | tee -a gpurun_out/${TAG}_probe_2cta.txt ;;
+    probe-pdl)     # programmatic dependent launch at small per-GPU batches (latency / strong-scaling points)
+      for cfg in "DS_TC_PDL=0 DS_PW_PDL=0" "DS_TC_PDL=1 DS_PW_PDL=1" "DS_TC_PDL=1 DS_PW_PDL=0"; do
+        for b in "--config lat1" "--config lat16" "--batch 128" "--batch 512" "--batch 1024"; do
+          env $cfg timeout 300 python bench.py $b --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', '$b', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks']['sm_mhz'])"
+        done
+      done 2>&1 | tee gpurun_out/${TAG}_probe_pdl.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
