@@ -1186,7 +1186,14 @@ extern "C" int ds_test_gemm_trace(const void* a_dev, const void* w_dev, const fl
   CK(cudaMemset(tr, 0, 256 * 8 * sizeof(unsigned long long)));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 3; ++i) launch_gemm_tc(p, M, 0);
+  int le = 0;
+  for (int i = 0; i < 3; ++i) le |= launch_gemm_tc(p, M, 0);
+  if (le) {       // launch errors are not sticky: without this check a refused launch reads as a 1 us kernel
+    cudaFree(tr);
+    tc_plan_destroy(p);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return fail(DS_ERR_CUDA, "trace GEMM launch failed: %s", cudaGetErrorString((cudaError_t)le));
+  }
   cudaEventRecord(e0, 0);
   for (int i = 0; i < reps; ++i) launch_gemm_tc(p, M, 0);
   cudaEventRecord(e1, 0);

@@ -59,7 +59,7 @@ struct TcEpi {
   float* d32;            // row-major plain kernel: fp32 output accumulated with atomics (split-K weight-gradient GEMMs)
   int ksplit;            // ... number of K splits (work units = tiles x ksplit)
   int wide_pass1;        // channels-on-lanes kernel, N = 12: statistics pass reads its 48 TMEM columns with x32 + x16 loads
-  int two_cta;           // channels-on-lanes kernel, cluster of 2: cta_group::2 MMAs (bit 0 on, bit 1 token halves swapped, bit 2 shallow ring) (DS_GNT_2CTA)
+  int two_cta;           // channels-on-lanes kernel, cluster of 2: cta_group::2 MMAs (bit 0 on, bit 2 shallow operand ring) (DS_GNT_2CTA)
   int uni_issue;         // producer / MMA warps run their loops warp-uniformly and elect the issuing lane (DS_TC_UNI)
   int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
@@ -768,7 +768,9 @@ __device__ __forceinline__ void stsm_x2_t(uint32_t addr, uint32_t r0, uint32_t r
   asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
 }
 
-template <int NOBJ, bool PAIR, int SC_, bool SP>
+// TWO: the CTA-pair instantiation (cta_group::2 instructions; must be launched with a cluster of 2 -- the driver
+// refuses a plain launch of a kernel that contains them, so the single-CTA path is a separate instantiation)
+template <int NOBJ, bool PAIR, int SC_, bool SP, bool TWO = false>
 // 18 warps = 5 on the fullest SM sub-partition: 16384 / (5 * 32) = 102 registers per thread at most
 __global__ void __maxnreg__(96)
 k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x0,
@@ -811,7 +813,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   //   empty[s]   both CTAs: 1 arrival each from the leader's multicast commit
   //   tfull[b]   both CTAs: 1 arrival each from the leader's multicast commit
   //   tempty[b]  leader only: 2 x 16 arrivals (the epilogue warps of both CTAs)
-  const bool two = epi.two_cta != 0 && cs == 2;
+  constexpr bool two = TWO;
   // operand ring geometry: the CTA pair stages only half of the token tile per CTA, so the same shared memory holds
   // more (smaller) stages
   const bool deep = two && !(epi.two_cta & 4);         // DS_GNT_2CTA |= 4: keep the single-CTA ring geometry (A/B)
@@ -833,7 +835,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    if (two) {       // collective over the pair: warp 1 of both CTAs
+    if constexpr (TWO) {       // collective over the pair: warp 1 of both CTAs
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                    "n"(Cfg::TMEM_COLS)
                    : "memory");
@@ -880,11 +882,11 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           const uint32_t sa = base + stage * stb;
           const CUtensorMap* tmx = kb < epi.kb0 ? &tm_x0 : &tm_x1;
           const int kx = (kb < epi.kb0 ? kb : kb - epi.kb0) * BK;
-          if constexpr (UNI) {
-            if (two) {      // CTA pair: own weight tile + own half of the token tile, bytes counted on the leader's barrier
+          if constexpr (UNI && TWO) {
+            {               // CTA pair: own weight tile + own half of the token tile, bytes counted on the leader's barrier
               if (crank == 0) mbar_expect_tx_r<true>(full_bar(stage), Cfg::STAGE_TX_2SM);
               tma_load_2d_2sm_elect(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
-              tma_load_2d_2sm_elect(sa + A_BYTES, tmx, kx, m0 + int(crank ^ uint32_t((epi.two_cta >> 1) & 1)) * (Cfg::UN / 2),
+              tma_load_2d_2sm_elect(sa + A_BYTES, tmx, kx, m0 + int(crank) * (Cfg::UN / 2),
                                     full_bar(stage));
               if (++stage == nst) { stage = 0; phase ^= 1u; }
               continue;
@@ -934,8 +936,8 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           const uint32_t sa = base + stage * stb;
           const uint64_t adesc = umma_desc(sa, epi.desc_hi);                // weights: the M operand
           const uint64_t bdesc = umma_desc(sa + A_BYTES, epi.desc_hi);      // activations: the N operand
-          if constexpr (UNI) {
-            if (two) {
+          if constexpr (UNI && TWO) {
+            {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k)
                 umma_issue_2sm_elect(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC_2SM, (kb | k) != 0);
@@ -951,7 +953,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           else umma_arrive_mc<UNI>(empty_bar(stage), cmask);   // ... in every CTA of the cluster
           if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
-        if (UNI && two) umma_arrive_2sm_mc_elect(tfull_bar(ab), 3);     // both CTAs' halves of the accumulator are complete
+        if constexpr (UNI && TWO) umma_arrive_2sm_mc_elect(tfull_bar(ab), 3);     // both CTAs' halves of the accumulator are complete
         else umma_arrive<UNI>(tfull_bar(ab));
         if (++ab == 2) { ab = 0; aphase ^= 1u; }
       }
@@ -1210,7 +1212,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           if constexpr (SP) {      // the accumulator has been read: the next-but-one tile's MMAs may start already
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (two) mbar_arrive_leader(tempty_bar(ab)); else mbar_arrive(tempty_bar(ab)); }
+            if (lane == 0) { if constexpr (TWO) mbar_arrive_leader(tempty_bar(ab)); else mbar_arrive(tempty_bar(ab)); }
           }
         }
         if constexpr (FM != 4) epi_bar();
@@ -1288,7 +1290,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
             tc_fence_before();
             __syncwarp();
             // accumulator drained: the next tile's MMAs may start (CTA pair: counted on the leader's barrier)
-            if (lane == 0) { if (two) mbar_arrive_leader(tempty_bar(ab)); else mbar_arrive(tempty_bar(ab)); }
+            if (lane == 0) { if constexpr (TWO) mbar_arrive_leader(tempty_bar(ab)); else mbar_arrive(tempty_bar(ab)); }
           }
           }
           if constexpr (FM == 1) {
@@ -1417,7 +1419,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
   if (cs > 1) cluster_sync_all();        // no CTA leaves while peers may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    if (two) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    if constexpr (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
@@ -1474,6 +1476,8 @@ bool tc_runtime_available(char* err, int err_len) {
   cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<21, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<12, false, 20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false, 20>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<21, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        GntCfg<12, false, 0, true>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
@@ -1548,10 +1552,20 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   int gnt_cs = 1;
   if (gnt) {
     if (const char* e = getenv("DS_GNT_CLUSTER")) gnt_cs = atoi(e);
-    if (gnt_two_cta()) gnt_cs = 2;                 // CTA-pair MMAs need the cluster of 2
-    if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
   }
   const int gnt_sc20 = gnt_scenes_per_tile(g.n_obj) == 20;
+  // CTA-pair MMAs (cta_group::2): DS_GNT_2CTA = 0 off, 1 wherever the shape allows, 2 (default) for K >= 1024 only --
+  // measured on B200 (profiles/round2_probe_2cta.txt): the K = 1024 skip convs gain 15 % (66.3 -> 56.6 us), the
+  // K = 512 blocks do not (39.2 us either way; with a residual the pair's lock-step costs 3 us)
+  int two_cta = 0;
+  if (gnt && !gnt_sc20 && tc_uniform_issue() && (g.N / BM) % 2 == 0) {
+    const int mode = gnt_two_cta() & 3;
+    if (mode == 1 || (mode == 2 && K >= 1024)) two_cta = 1 | (gnt_two_cta() & 4);
+  }
+  if (gnt) {
+    if (two_cta) gnt_cs = 2;                       // the pair is a cluster of 2
+    if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
+  }
   const int gnt_un = g.n_obj == 21 ? GntCfg<21, true>::UN : (gnt_sc20 ? GntCfg<12, false, 20>::UN : GntCfg<12, true>::UN);
   const int gnt_tok = g.n_obj == 21 ? GntCfg<21, true>::TOK : (gnt_sc20 ? GntCfg<12, false, 20>::TOK : GntCfg<12, true>::TOK);
   const uint32_t act_box = gnt ? uint32_t(gnt_un / gnt_cs) : uint32_t(BM);     // rows of one activation load
@@ -1602,7 +1616,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     static const int wide = getenv("DS_GNT_WIDE1") ? atoi(getenv("DS_GNT_WIDE1")) : 0;
     p->epi.wide_pass1 = wide;
     p->epi.uni_issue = tc_uniform_issue();
-    p->epi.two_cta = (gnt && gnt_cs == 2 && p->epi.uni_issue) ? gnt_two_cta() : 0;
+    p->epi.two_cta = (gnt && gnt_cs == 2) ? two_cta : 0;
   }
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
@@ -1672,13 +1686,13 @@ static bool gnt_nobj_ok(int n_obj) {
 bool tc_gnt_plain_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0; }
 bool tc_gnt_supported(int n_obj, int N) { return gnt_nobj_ok(n_obj) && N % BM == 0 && N <= GntCfg<12, true>::CHAN_MAX_N; }
 
-// DS_GNT_2CTA: 0 off, 1 cta_group::2 MMAs over a cluster of 2 (3: token-tile halves swapped -- bring-up aid)
+// DS_GNT_2CTA: 0 off, 1 always, 2 by shape (default); | 4: keep the single-CTA operand-ring geometry (A/B)
 static int gnt_two_cta() {
-  static const int v = getenv("DS_GNT_2CTA") ? atoi(getenv("DS_GNT_2CTA")) : 0;
+  static const int v = getenv("DS_GNT_2CTA") ? atoi(getenv("DS_GNT_2CTA")) : 2;
   return v;
 }
 
-template <int NOBJ, bool PAIR, int SC_ = 0, bool SP = false>
+template <int NOBJ, bool PAIR, int SC_ = 0, bool SP = false, bool TWO = false>
 static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cudaStream_t s) {
   using Cfg = GntCfg<NOBJ, PAIR, SC_, SP>;
   const int n_scenes = epi.M / NOBJ;
@@ -1710,14 +1724,14 @@ static int launch_gnt(const TcGemmPlan* p, const TcEpi& epi, int* flag_dev, cuda
       cfg.numAttrs = na;
       cfg.gridDim = dim3(max_cl * cs);
       int n = 0;
-      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<NOBJ, PAIR, SC_, SP>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
+      cached = (cudaOccupancyMaxActiveClusters(&n, k_gemm_gnt<NOBJ, PAIR, SC_, SP, TWO>, &cfg) == cudaSuccess && n > 0) ? n : max_cl;
     }
     if (cached < max_cl) max_cl = cached;
   }
   cfg.attrs = na ? attr : nullptr;
   cfg.numAttrs = na;
   cfg.gridDim = dim3((total < max_cl ? total : max_cl) * cs);
-  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<NOBJ, PAIR, SC_, SP>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_gnt<NOBJ, PAIR, SC_, SP, TWO>, p->tm_w, p->tm_a0, p->tm_a1, epi, flag_dev);
 }
 
 int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
@@ -1729,6 +1743,7 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
     // GroupNorm statistics exchange: 0 (default) two CTA-wide barriers, 1 warp-pair local (named 64-thread barriers);
     // A/B on one box (profiles/round2_gnt_ab.txt): no difference (39.3 / 43.2 / 66.3 us vs 40.0 / 43.2 / 66.0 us)
     static const int pair = getenv("DS_GNT_PAIR") ? atoi(getenv("DS_GNT_PAIR")) : 0;
+    if (epi.two_cta && p->cluster == 2) return epi.n_obj == 21 ? launch_gnt<21, false, 0, false, true>(p, epi, fd, s) : launch_gnt<12, false, 0, false, true>(p, epi, fd, s);
     if (epi.n_obj == 12 && gnt_scenes_per_tile(12) == 20) return launch_gnt<12, false, 20>(p, epi, fd, s);
     // DS_GNT_SPILL=1 (A/B switch, N = 12): single TMEM read, normalisation pass from shared memory
     static const int spill = getenv("DS_GNT_SPILL") ? atoi(getenv("DS_GNT_SPILL")) : 0;

@@ -78,25 +78,17 @@ run_task() {
         echo "== DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf"
         DS_GNT_PAIR=$pair DS_GNT_PREFETCH=$pf GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -E "^(GNT|T qkv|T to_out|T enc.l1)" | grep "M=49152"
       done; done | tee gpurun_out/${TAG}_probe_ab.txt ;;
-    probe-uni)     # A/B of the warp-uniform producer / MMA issue (DS_TC_UNI) with numeric checks, then short benches
-      for u in 0 1; do
-        echo "== DS_TC_UNI=$u"
-        DS_TC_UNI=$u GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "M=49152|MISMATCH|FAILED" | grep -v "^--"
+    probe-uni)     # A/B of the warp-uniform issue (DS_TC_UNI) and the CTA-pair policy (DS_GNT_2CTA) with numeric checks, then short benches
+      for cfg in "DS_TC_UNI=0 DS_GNT_2CTA=0" "DS_TC_UNI=1 DS_GNT_2CTA=0" "DS_TC_UNI=1 DS_GNT_2CTA=2" "DS_TC_UNI=1 DS_GNT_2CTA=1"; do
+        echo "== $cfg"
+        env $cfg GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "M=49152|MISMATCH|FAILED" | grep -v "^--" | cut -c1-220
       done | tee gpurun_out/${TAG}_probe_uni.txt
-      for cfg in "DS_TC_UNI=0" "DS_TC_UNI=1" "DS_TC_UNI=1 DS_GNT_SC=20" "DS_TC_UNI=1 DS_GNT_SPILL=1" "DS_TC_UNI=1 DS_GNT_CLUSTER=2" "DS_TC_UNI=1 DS_TC_PDL=1"; do
-        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
-      done | tee -a gpurun_out/${TAG}_probe_uni.txt ;;
-    probe-2cta)    # bring-up of the cta_group::2 mode of k_gemm_gnt: numeric checks + timings, then short benches
-      for v in 0 1 3 5; do
-        echo "== DS_GNT_2CTA=$v"
-        DS_GNT_2CTA=$v GNT_ONLY=1 GNT_CHECKS=1 timeout 200 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "^GNT|check GNT|MISMATCH|FAILED|rror" | grep -v "^--" | cut -c1-200
-      done | tee gpurun_out/${TAG}_probe_2cta.txt
-      for cfg in "DS_GNT_2CTA=0" "DS_GNT_2CTA=1" "DS_GNT_2CTA=3" "DS_GNT_2CTA=5"; do
-        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])"
-      done 2>&1 | tee -a gpurun_out/${TAG}_probe_2cta.txt ;;
+      for cfg in "DS_TC_UNI=0 DS_GNT_2CTA=0" "DS_TC_UNI=1 DS_GNT_2CTA=0" "DS_TC_UNI=1 DS_GNT_2CTA=2" "DS_TC_UNI=1 DS_GNT_2CTA=1"; do
+        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d['parity_max_abs'], d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
+      done 2>&1 | tee -a gpurun_out/${TAG}_probe_uni.txt ;;
     probe-pdl)     # programmatic dependent launch at small per-GPU batches (latency / strong-scaling points)
-      for cfg in "DS_TC_PDL=0 DS_PW_PDL=0" "DS_TC_PDL=1 DS_PW_PDL=1" "DS_TC_PDL=1 DS_PW_PDL=0"; do
-        for b in "--config lat1" "--config lat16" "--batch 128" "--batch 512" "--batch 1024"; do
+      for cfg in "DS_TC_PDL=0 DS_PW_PDL=0" "DS_TC_PDL=1 DS_PW_PDL=1"; do
+        for b in "--config lat1" "--batch 128" "--batch 512" "--batch 1024"; do
           env $cfg timeout 300 python bench.py $b --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', '$b', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks']['sm_mhz'])"
         done
       done 2>&1 | tee gpurun_out/${TAG}_probe_pdl.txt ;;
