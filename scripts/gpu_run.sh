@@ -92,6 +92,15 @@ run_task() {
           env $cfg timeout 300 python bench.py $b --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', '$b', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks']['sm_mhz'])"
         done
       done 2>&1 | tee gpurun_out/${TAG}_probe_pdl.txt ;;
+    probe-epi)     # epilogue variants of k_gemm_gnt again, now that the MMA side is fast (uniform issue): probe + short benches
+      for cfg in "DS_GNT_SPILL=0" "DS_GNT_SPILL=1" "DS_GNT_SC=20" "DS_GNT_PAIR=1"; do
+        echo "== $cfg"
+        env $cfg GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "^GNT.*M=49152|MISMATCH|FAILED" | grep -v "^--" | cut -c1-220
+      done | tee gpurun_out/${TAG}_probe_epi.txt
+      for cfg in "DS_TC_UNI=1" "DS_TC_UNI=0 DS_GNT_2CTA=0" "DS_GNT_SPILL=1" "DS_GNT_SC=20" "DS_TC_PDL=1 DS_PW_PDL=1" "DS_TC_PDL=1 DS_PW_PDL=1 BATCH=2048" "BATCH=2048"; do
+        b=4096; case "$cfg" in *BATCH=2048*) b=2048;; esac
+        env $cfg timeout 300 python bench.py --batch $b --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
+      done 2>&1 | tee -a gpurun_out/${TAG}_probe_epi.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
