@@ -60,6 +60,7 @@ struct TcEpi {
   int ksplit;            // ... number of K splits (work units = tiles x ksplit)
   int wide_pass1;        // channels-on-lanes kernel, N = 12: statistics pass reads its 48 TMEM columns with x32 + x16 loads
   int two_cta;           // channels-on-lanes kernel, cluster of 2: cta_group::2 MMAs (bit 0 on, bit 2 shallow operand ring) (DS_GNT_2CTA)
+  int l2_prefetch;       // producers L2-prefetch the activation tile of their next work unit (A/B switch DS_TC_L2PF)
   int uni_issue;         // producer / MMA warps run their loops warp-uniformly and elect the issuing lane (DS_TC_UNI)
   int res_prefetch;      // channels-on-lanes kernel: L2-prefetch the next tile's residual rows (A/B switch DS_GNT_PREFETCH)
   unsigned long long* trace;   // optional [grid][8] cycle counters (bring-up / profiling aid), else nullptr
@@ -195,6 +196,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
           if (kb < epi.kb0) tma_load_2d_r<UNI>(sa, &tm_a0, kb * BK, m0, full_bar(stage));
           else tma_load_2d_r<UNI>(sa, &tm_a1, (kb - epi.kb0) * BK, m0, full_bar(stage));
+          if (epi.l2_prefetch && cs == 1 && n_idx == 0 && unit + num_clusters < tiles_mn) {      // see k_gemm_gnt
+            const int m1 = ((unit + num_clusters) / num_n) * epi.tile_rows;
+            if (kb < epi.kb0) tma_prefetch_2d_r<UNI>(&tm_a0, kb * BK, m1);
+            else tma_prefetch_2d_r<UNI>(&tm_a1, (kb - epi.kb0) * BK, m1);
+          }
           if (cs == 1) {
             tma_load_2d_r<UNI>(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN, full_bar(stage));
           } else {
@@ -896,6 +902,11 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
           tma_load_2d_r<UNI>(sa, &tm_w, kb * BK, ct * BM, full_bar(stage));
           if (cs == 1) {
             tma_load_2d_r<UNI>(sa + A_BYTES, tmx, kx, m0, full_bar(stage));
+            // DS_TC_L2PF: pull the NEXT token tile of this CTA towards L2 a whole tile time ahead (the activations were
+            // written by the previous kernel and are only partly L2-resident); the channel-tile-0 CTA does it for the
+            // CTAs that share the token tile
+            if (epi.l2_prefetch && ct == 0 && tile + unit_step < total)
+              tma_prefetch_2d_r<UNI>(tmx, kx, ((tile + unit_step) / cgn) * Cfg::TOK);
           } else {
             const int rows = Cfg::UN / int(cs);      // this CTA's slice of the activation tile, broadcast to the cluster
             tma_load_2d_mc_r<UNI>(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), tmx, kx, m0 + int(crank) * rows,
@@ -1478,6 +1489,8 @@ bool tc_runtime_available(char* err, int err_len) {
   cudaFuncSetAttribute(k_gemm_gnt<12, false, 20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false, 20>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<21, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false, 0, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_gnt<12, true, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, true>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        GntCfg<12, false, 0, true>::SMEM_BYTES);
   g_encode = (PFN_encodeTiled)fn;
@@ -1616,6 +1629,8 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     static const int wide = getenv("DS_GNT_WIDE1") ? atoi(getenv("DS_GNT_WIDE1")) : 0;
     p->epi.wide_pass1 = wide;
     p->epi.uni_issue = tc_uniform_issue();
+    static const int l2pf = getenv("DS_TC_L2PF") ? atoi(getenv("DS_TC_L2PF")) : 0;
+    p->epi.l2_prefetch = l2pf;
     p->epi.two_cta = (gnt && gnt_cs == 2) ? two_cta : 0;
   }
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
@@ -1743,7 +1758,13 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
     // GroupNorm statistics exchange: 0 (default) two CTA-wide barriers, 1 warp-pair local (named 64-thread barriers);
     // A/B on one box (profiles/round2_gnt_ab.txt): no difference (39.3 / 43.2 / 66.3 us vs 40.0 / 43.2 / 66.0 us)
     static const int pair = getenv("DS_GNT_PAIR") ? atoi(getenv("DS_GNT_PAIR")) : 0;
-    if (epi.two_cta && p->cluster == 2) return epi.n_obj == 21 ? launch_gnt<21, false, 0, false, true>(p, epi, fd, s) : launch_gnt<12, false, 0, false, true>(p, epi, fd, s);
+    if (epi.two_cta && p->cluster == 2) {
+      // A/B: the epilogue variants combined with the CTA pair (N = 12 only)
+      static const int spill2 = getenv("DS_GNT_SPILL") ? atoi(getenv("DS_GNT_SPILL")) : 0;
+      if (epi.n_obj == 12 && spill2) return launch_gnt<12, false, 0, true, true>(p, epi, fd, s);
+      if (epi.n_obj == 12 && pair) return launch_gnt<12, true, 0, false, true>(p, epi, fd, s);
+      return epi.n_obj == 21 ? launch_gnt<21, false, 0, false, true>(p, epi, fd, s) : launch_gnt<12, false, 0, false, true>(p, epi, fd, s);
+    }
     if (epi.n_obj == 12 && gnt_scenes_per_tile(12) == 20) return launch_gnt<12, false, 20>(p, epi, fd, s);
     // DS_GNT_SPILL=1 (A/B switch, N = 12): single TMEM read, normalisation pass from shared memory
     static const int spill = getenv("DS_GNT_SPILL") ? atoi(getenv("DS_GNT_SPILL")) : 0;

@@ -12,7 +12,7 @@
 
 namespace ds {
 
-static constexpr int PDL_DEFAULT_MODE = 0;      // 0 off / 1 on / 2 automatic by launch size (see kernels.cuh)
+static constexpr int PDL_DEFAULT_MODE = 2;      // 0 off / 1 on / 2 automatic by launch size (see kernels.cuh)
 
 // Programmatic dependent launch for the pointwise kernels of the step program: launched with the PDL attribute, a
 // kernel may be scheduled while the previous kernel in the stream (a GEMM that issued griddepcontrol.launch_dependents)
@@ -22,7 +22,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 bool pdl_enabled(int kind, int64_t rows) {
   static const int mode[2] = {getenv("DS_TC_PDL") ? atoi(getenv("DS_TC_PDL")) : PDL_DEFAULT_MODE,
                               getenv("DS_PW_PDL") ? atoi(getenv("DS_PW_PDL")) : PDL_DEFAULT_MODE};
-  static const int64_t auto_rows = getenv("DS_PDL_ROWS") ? atoll(getenv("DS_PDL_ROWS")) : 16384;
+  static const int64_t auto_rows = getenv("DS_PDL_ROWS") ? atoll(getenv("DS_PDL_ROWS")) : 32768;
   const int m = mode[kind != 0];
   return m == 2 ? rows <= auto_rows : m != 0;
 }

@@ -245,6 +245,20 @@ __device__ __forceinline__ void tma_load_2d_mc_r(uint32_t dst, const CUtensorMap
   }
 }
 
+// L2 prefetch of a tile a TMA load will fetch later (no shared-memory destination, no barrier)
+template <bool UNI>
+__device__ __forceinline__ void tma_prefetch_2d_r(const CUtensorMap* map, int c0, int c1) {
+  if constexpr (UNI) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}" ::"l"(map), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+  }
+}
+
 // ---- CTA pair (cta_group::2): one UMMA of M = 256 spans the two SMs of a cluster of 2 ------------------------------
 // Each CTA keeps its own 128 rows of the M operand and HALF of the N operand's rows in its own shared memory (same
 // offsets in both CTAs); the even ("leader") CTA issues the MMAs for the pair, each CTA's TMEM receives its 128 rows of

@@ -101,6 +101,14 @@ run_task() {
         b=4096; case "$cfg" in *BATCH=2048*) b=2048;; esac
         env $cfg timeout 300 python bench.py --batch $b --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
       done 2>&1 | tee -a gpurun_out/${TAG}_probe_epi.txt ;;
+    probe-l2pf)    # L2 prefetch of the next activation tile (DS_TC_L2PF), pair-local statistics again; short benches
+      for cfg in "DS_TC_L2PF=0" "DS_TC_L2PF=1"; do
+        echo "== $cfg"
+        env $cfg GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "M=49152|MISMATCH|FAILED" | grep -v "^--\|^   prod" | cut -c1-220
+      done | tee gpurun_out/${TAG}_probe_l2pf.txt
+      for cfg in "DS_TC_L2PF=1" "DS_GNT_PAIR=1" "DS_TC_L2PF=1 DS_GNT_PAIR=1" "DS_TC_L2PF=0"; do
+        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
+      done 2>&1 | tee -a gpurun_out/${TAG}_probe_l2pf.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
