@@ -109,6 +109,14 @@ run_task() {
       for cfg in "DS_TC_L2PF=1" "DS_GNT_PAIR=1" "DS_TC_L2PF=1 DS_GNT_PAIR=1" "DS_TC_L2PF=0"; do
         env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
       done 2>&1 | tee -a gpurun_out/${TAG}_probe_l2pf.txt ;;
+    probe-pairepi) # CTA pair everywhere combined with the epilogue variants (single TMEM read / pair-local statistics)
+      for cfg in "DS_GNT_2CTA=1 DS_GNT_SPILL=1" "DS_GNT_2CTA=1 DS_GNT_PAIR=1"; do
+        echo "== $cfg"
+        env $cfg GNT_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -A1 -E "^GNT.*M=49152|check GNT|MISMATCH|FAILED" | grep -v "^--" | cut -c1-220
+      done | tee gpurun_out/${TAG}_probe_pairepi.txt
+      for cfg in "DS_GNT_2CTA=1 DS_GNT_SPILL=1" "DS_GNT_2CTA=1 DS_GNT_PAIR=1"; do
+        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
+      done 2>&1 | tee -a gpurun_out/${TAG}_probe_pairepi.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
     *) echo "unknown task $task"; return 2 ;;
