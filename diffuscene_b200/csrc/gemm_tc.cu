@@ -1755,9 +1755,11 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   if (p->gnt) {
     int* fd = nullptr;
     cudaHostGetDevicePointer((void**)&fd, g_err_flag, 0);
-    // GroupNorm statistics exchange: 0 (default) two CTA-wide barriers, 1 warp-pair local (named 64-thread barriers);
-    // A/B on one box (profiles/round2_gnt_ab.txt): no difference (39.3 / 43.2 / 66.3 us vs 40.0 / 43.2 / 66.0 us)
-    static const int pair = getenv("DS_GNT_PAIR") ? atoi(getenv("DS_GNT_PAIR")) : 0;
+    // GroupNorm statistics exchange: 0 two CTA-wide barriers, 1 (default) warp-pair local (named 64-thread barriers).
+    // A/B on one box: no difference while the MMA issue was the slow side (profiles/round2_gnt_ab.txt: 39.3 / 43.2 / 66.3
+    // us vs 40.0 / 43.2 / 66.0 us); with the warp-uniform issue the residual blocks gain (41.5 -> 40.1 us) and the
+    // whole sample 1.1 % (900.5 -> 910.8 scenes/s, profiles/round2_probe_l2pf.txt)
+    static const int pair = getenv("DS_GNT_PAIR") ? atoi(getenv("DS_GNT_PAIR")) : 1;
     if (epi.two_cta && p->cluster == 2) {
       // A/B: the epilogue variants combined with the CTA pair (N = 12 only)
       static const int spill2 = getenv("DS_GNT_SPILL") ? atoi(getenv("DS_GNT_SPILL")) : 0;
