@@ -456,10 +456,12 @@ def main():
                 tj = json.load(f)
             res["roofline"]["traffic"] = tj["step_dram_bytes"]
             res["roofline"]["traffic_source"] = "profiles/%s (ncu dram__bytes_read+write, one step)" % os.path.basename(tpath)
-            k = next((v for n, v in tj["kernels"].items() if n.startswith("k_gemm_gnt<%d" % N_OBJ)), None)
-            if k and dom:
-                res["roofline"]["dominant_kernel"]["traffic"] = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"]
-                res["roofline"]["dominant_kernel"]["ncu_share_of_step"] = k["time_ns"] / tj["step_time_ns"]
+            # every instantiation of the kernel that ran in the step (single-CTA and CTA-pair)
+            ks = [v for n, v in tj["kernels"].items() if n.startswith("k_gemm_gnt<%d" % N_OBJ)]
+            if ks and dom:
+                res["roofline"]["dominant_kernel"]["traffic"] = (
+                    sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in ks) / sum(k["launches"] for k in ks))
+                res["roofline"]["dominant_kernel"]["ncu_share_of_step"] = sum(k["time_ns"] for k in ks) / tj["step_time_ns"]
         if args.profile_ops:
             tot = sum(u for _, u in ops)
             sys.stderr.write("per-op device time (us), total %.1f\n" % tot)
