@@ -98,9 +98,20 @@ struct TcCfg {
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
                                     (uint32_t(BM >> 4) << 24);
+  // CTA pair (cta_group::2): M = 256 = the two CTAs' token tiles, N = BN (half of the weight tile's rows in each CTA)
+  static constexpr uint32_t IDESC_2SM = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
+                                        (uint32_t((2 * BM) >> 4) << 24);
+  static constexpr int STAGE_BYTES_2SM = A_BYTES + B_BYTES / 2;
+  static constexpr int STAGE_TX_2SM = 2 * STAGE_BYTES_2SM;
+  static constexpr int MAX_STAGES = 6;       // barrier slots reserved behind the ring
+  static constexpr int STAGES_2SM = (STAGES * STAGE_BYTES) / STAGE_BYTES_2SM < MAX_STAGES ? (STAGES * STAGE_BYTES) / STAGE_BYTES_2SM : MAX_STAGES;
+  static_assert(STAGES <= MAX_STAGES && STAGE_BYTES_2SM % 1024 == 0, "ring geometry");
 };
 
-template <int BN, bool GN>
+// TWO: the CTA-pair instantiation (see k_gemm_gnt): one tcgen05.mma.cta_group::2 of M = 256 covers the two consecutive
+// token tiles of a cluster of 2; each CTA loads its own token tile and HALF of the weight tile, the even CTA issues.
+// Per CTA and k-block 32 KB instead of 48 KB come from L2 for the same MMA work (BN = 256) and the ring holds 6 stages.
+template <int BN, bool GN, bool TWO = false>
 // 10 warps occupy 12 warp slots of the register file (allocation is per 4 warps): 65536 / (12 * 32) = 170 registers
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
@@ -112,10 +123,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::MAX_STAGES + 4);
   uint8_t* const scratch = base_ptr + Cfg::SCRATCH_OFF;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   float* const bias_s = reinterpret_cast<float*>(scratch);          // [N] bias (both epilogues)
@@ -141,23 +152,34 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     tma_prefetch_desc(&tm_a0);
     tma_prefetch_desc(&tm_a1);
     tma_prefetch_desc(&tm_w);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    // CTA pair: full[] and tempty[] are used in the leader only (its own expect_tx covers both CTAs' bytes; 2 x 8
+    // epilogue warps arrive on its tempty), empty[] / tfull[] get one arrival each from the leader's multicast commits
+    for (int s = 0; s < Cfg::MAX_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), cs);       // every CTA of the cluster must have consumed the slot
+      mbar_init(empty_bar(s), TWO ? 1 : cs);       // multicast mode: every CTA of the cluster must have consumed the slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), EPI_WARPS);
+      mbar_init(tempty_bar(b), TWO ? 2 * EPI_WARPS : EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "n"(Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
+  constexpr int nst = TWO ? Cfg::STAGES_2SM : Cfg::STAGES;
+  constexpr uint32_t stb = TWO ? uint32_t(Cfg::STAGE_BYTES_2SM) : uint32_t(Cfg::STAGE_BYTES);
   tc_fence_before();
   __syncthreads();
   if (cs > 1) cluster_sync_all();        // peers' barriers are initialised before anyone signals them
@@ -192,8 +214,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           unsigned long long t0 = epi.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u, err_flag, 1);
           if (epi.trace) tw += clock64() - t0;
+          const uint32_t sa = base + stage * stb;
+          if constexpr (UNI && TWO) {      // CTA pair: own token tile + own half of the weight tile, bytes counted on the leader
+            if (crank == 0) mbar_expect_tx_r<true>(full_bar(stage), Cfg::STAGE_TX_2SM);
+            if (kb < epi.kb0) tma_load_2d_2sm_elect(sa, &tm_a0, kb * BK, m0, full_bar(stage));
+            else tma_load_2d_2sm_elect(sa, &tm_a1, (kb - epi.kb0) * BK, m0, full_bar(stage));
+            tma_load_2d_2sm_elect(sa + A_BYTES, &tm_w, kb * BK, n_idx * BN + int(crank) * (BN / 2), full_bar(stage));
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_expect_tx_r<UNI>(full_bar(stage), Cfg::STAGE_BYTES);
-          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
           if (kb < epi.kb0) tma_load_2d_r<UNI>(sa, &tm_a0, kb * BK, m0, full_bar(stage));
           else tma_load_2d_r<UNI>(sa, &tm_a1, (kb - epi.kb0) * BK, m0, full_bar(stage));
           if (epi.l2_prefetch && cs == 1 && n_idx == 0 && unit + num_clusters < tiles_mn) {      // see k_gemm_gnt
@@ -208,7 +238,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
             tma_load_2d_mc_r<UNI>(sa + A_BYTES + uint32_t(crank) * uint32_t(rows * BK * 2), &tm_w, kb * BK,
                                   n_idx * BN + int(crank) * rows, full_bar(stage), cmask);
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
       }
       if (epi.trace && lane == 0) {
@@ -223,6 +253,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
     auto issuer = [&](auto uni_tag) {
       constexpr bool UNI = decltype(uni_tag)::value;
       if (!UNI && lane != 0) return;
+      if (TWO && crank != 0) return;                 // CTA pair: the even CTA issues for both
       int stage = 0;
       uint32_t phase = 0;
       int ab = 0;
@@ -240,9 +271,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           mbar_wait(full_bar(stage), phase, err_flag, 3);
           if (epi.trace) tw_f += clock64() - t0;
           tc_fence_after();
-          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sa = base + stage * stb;
           const uint64_t adesc = umma_desc(sa, epi.desc_hi);
           const uint64_t bdesc = umma_desc(sa + A_BYTES, epi.desc_hi);
+          if constexpr (UNI && TWO) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_issue_2sm_elect(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), Cfg::IDESC_2SM, ((kb - kb_lo) | k) != 0);
+            umma_arrive_2sm_mc_elect(empty_bar(stage), 3);     // the slot is free in BOTH CTAs
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
@@ -250,9 +289,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
           }
           if (cs == 1) umma_arrive<UNI>(empty_bar(stage));     // smem slot reusable once these MMAs have read it
           else umma_arrive_mc<UNI>(empty_bar(stage), cmask);   // ... in every CTA of the cluster
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
-        umma_arrive<UNI>(tfull_bar(ab));               // accumulator complete -> epilogue
+        if constexpr (UNI && TWO) umma_arrive_2sm_mc_elect(tfull_bar(ab), 3);     // both CTAs' halves are complete
+        else umma_arrive<UNI>(tfull_bar(ab));               // accumulator complete -> epilogue
         if (++ab == 2) { ab = 0; aphase ^= 1u; }
       }
       if (epi.trace && lane == 0) {
@@ -439,7 +479,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
       auto release_tmem = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(ab));   // accumulator buffer free: the next tile's MMAs may start
+        // accumulator buffer free: the next tile's MMAs may start (CTA pair: counted on the leader's barrier)
+        if (lane == 0) { if constexpr (TWO) mbar_arrive_leader(tempty_bar(ab)); else mbar_arrive(tempty_bar(ab)); }
         if (++ab == 2) { ab = 0; aphase ^= 1u; }
       };
 
@@ -630,8 +671,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUt
   if (cs > 1) cluster_sync_all();        // no CTA leaves while peers may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
-                 : "memory");
+    if constexpr (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -1439,6 +1480,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
 static int gnt_two_cta();
+static constexpr int TC_2CTA_DEFAULT = 0;      // row-major kernel: CTA pair off / on by default (DS_TC_2CTA)
 struct TcGemmPlan {
   CUtensorMap tm_a0, tm_a1, tm_w;
   TcEpi epi;
@@ -1482,6 +1524,7 @@ bool tc_runtime_available(char* err, int err_len) {
   cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(k_gemm_tc<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, false>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<12, true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, true>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<21, true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<21, true>::SMEM_BYTES);
   cudaFuncSetAttribute(k_gemm_gnt<12, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GntCfg<12, false>::SMEM_BYTES);
@@ -1579,6 +1622,13 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     if (two_cta) gnt_cs = 2;                       // the pair is a cluster of 2
     if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
   }
+  // row-major plain kernel, 128 x 256 tiles: DS_TC_2CTA = 0 off, 1 CTA pair for K >= DS_TC_2CTA_K (default 256)
+  int tc_two = 0;
+  if (!gnt && !gn && p->bn == 256 && tc_uniform_issue()) {
+    static const int m2 = getenv("DS_TC_2CTA") ? atoi(getenv("DS_TC_2CTA")) : TC_2CTA_DEFAULT;
+    static const int k2 = getenv("DS_TC_2CTA_K") ? atoi(getenv("DS_TC_2CTA_K")) : 256;
+    if (m2 && K >= k2) tc_two = 1;
+  }
   const int gnt_un = g.n_obj == 21 ? GntCfg<21, true>::UN : (gnt_sc20 ? GntCfg<12, false, 20>::UN : GntCfg<12, true>::UN);
   const int gnt_tok = g.n_obj == 21 ? GntCfg<21, true>::TOK : (gnt_sc20 ? GntCfg<12, false, 20>::TOK : GntCfg<12, true>::TOK);
   const uint32_t act_box = gnt ? uint32_t(gnt_un / gnt_cs) : uint32_t(BM);     // rows of one activation load
@@ -1588,6 +1638,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   p->cluster = 1;
   if (const char* e = getenv("DS_TC_CLUSTER")) p->cluster = atoi(e);
   if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) p->cluster = 1;
+  if (tc_two) p->cluster = 2;
   if (gnt) p->cluster = gnt_cs;
   if (ok) ok = encode_2d(&p->tm_w, g.w, K, g.N, g.ldw, gnt ? BM : p->bn / p->cluster, err, err_len);
   const int tile_rows = gnt ? gnt_tok : (gn ? (BM / g.n_obj) * g.n_obj : BM);
@@ -1631,7 +1682,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     p->epi.uni_issue = tc_uniform_issue();
     static const int l2pf = getenv("DS_TC_L2PF") ? atoi(getenv("DS_TC_L2PF")) : 0;
     p->epi.l2_prefetch = l2pf;
-    p->epi.two_cta = (gnt && gnt_cs == 2) ? two_cta : 0;
+    p->epi.two_cta = gnt ? ((gnt_cs == 2) ? two_cta : 0) : tc_two;
   }
   // bring-up overrides (hex), e.g. DS_TC_DESC_HI=0x4000404000010000
   if (const char* e = getenv("DS_TC_DESC_HI")) p->epi.desc_hi = strtoull(e, nullptr, 16);
@@ -1654,7 +1705,7 @@ int tc_plan_tiles(const TcGemmPlan* p, int M) {
   return ((num_m + p->cluster - 1) / p->cluster) * (p->epi.N / p->bn);
 }
 
-template <int BN, bool GN>
+template <int BN, bool GN, bool TWO = false>
 static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* flag_dev, cudaStream_t s) {
   const int cs = p->cluster;
   int max_cl = p->num_sms / cs;
@@ -1678,19 +1729,19 @@ static int launch_one(const TcGemmPlan* p, const TcEpi& epi, int total_ct, int* 
     cfg.numAttrs = 2;
   }
   if (cs > 1) {
-    static int cached[3][5] = {{0}};      // [kernel variant][cluster size]
-    const int kv = GN ? 2 : (BN == 256 ? 1 : 0);
+    static int cached[4][5] = {{0}};      // [kernel variant][cluster size]
+    const int kv = TWO ? 3 : (GN ? 2 : (BN == 256 ? 1 : 0));
     if (!cached[kv][cs]) {
       cfg.gridDim = dim3(p->num_sms / cs * cs);
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc<BN, GN>, &cfg) == cudaSuccess && n > 0) cached[kv][cs] = n;
+      if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc<BN, GN, TWO>, &cfg) == cudaSuccess && n > 0) cached[kv][cs] = n;
       else cached[kv][cs] = max_cl;
     }
     if (cached[kv][cs] < max_cl) max_cl = cached[kv][cs];
   }
   const int ncl = total_ct < max_cl ? total_ct : max_cl;
   cfg.gridDim = dim3(ncl * cs);
-  return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
+  return (int)cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, GN, TWO>, p->tm_a0, p->tm_a1, p->tm_w, epi, flag_dev);
 }
 
 // object counts the channels-on-lanes kernel is instantiated for (DS_GNT21=0 keeps N = 21 on the row-major kernel)
@@ -1780,6 +1831,7 @@ int launch_gemm_tc(const TcGemmPlan* p, int M, cudaStream_t s) {
   int* flag_dev = nullptr;
   cudaHostGetDevicePointer((void**)&flag_dev, g_err_flag, 0);
   if (p->gn) return launch_one<256, true>(p, epi, total_ct, flag_dev, s);
+  if (p->bn == 256 && epi.two_cta && p->cluster == 2) return launch_one<256, false, true>(p, epi, total_ct, flag_dev, s);
   if (p->bn == 256) return launch_one<256, false>(p, epi, total_ct, flag_dev, s);
   return launch_one<128, false>(p, epi, total_ct, flag_dev, s);
 }

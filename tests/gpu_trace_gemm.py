@@ -79,6 +79,22 @@ def run(M, N, K, n_obj=0, res=False, tag="", gnt=False, check=False, plain_act=N
 cl = os.environ.get("DS_TC_CLUSTER", "1")
 print("cluster size", cl)
 M = 49152
+if os.environ.get("PLAIN_ONLY"):      # row-major plain kernel (k_gemm_tc): numeric checks incl. odd tile counts, then timings
+    for m_chk in (128 * 5, 128 * 5 - 37, 12 * 1000, 128 * 301):
+        run(m_chk, 512, 512, tag="plain 512x512", check=True)
+        run(m_chk, 512, 512, res=True, tag="plain+res", check=True)
+        run(m_chk, 1024, 512, tag="plain N=1024", check=True)
+        run(m_chk, 512, 1024, tag="plain K=1024", check=True)
+        run(m_chk, 384, 512, tag="plain N=384 (BN=128)", check=True)
+        run(m_chk, 512, 128, tag="plain K=128", check=True)
+    run(M, 512, 128, tag="to_out K=128")
+    run(M, 1536, 64, tag="enc.l0")
+    run(M, 1024, 512, tag="enc.l1")
+    run(M, 512, 3072, tag="encoder K=3072")
+    run(M, 3072, 512, tag="dec.l0")
+    run(M, 512, 1024, tag="plain 512x1024")
+    run(M, 512, 512, tag="plain 512x512")
+    sys.exit(0)
 if os.environ.get("GNT_ONLY"):
     for m_chk in (12 * 16 * 3, 12 * 1000):      # whole tiles / ragged last tile
         run(m_chk, 512, 512, n_obj=12, tag="GN", check=True)
