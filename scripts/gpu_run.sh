@@ -122,8 +122,8 @@ run_task() {
         echo "== $cfg"
         env $cfg PLAIN_ONLY=1 timeout 300 python tests/gpu_trace_gemm.py 2>&1 | grep -E "check|M=49152|MISMATCH|FAILED|rror|mma_wait" | grep -v "OK$" | cut -c1-220
       done | tee gpurun_out/${TAG}_probe_tc2.txt
-      for cfg in "DS_TC_2CTA=1" "DS_TC_2CTA=0" "DS_TC_2CTA=1 DS_TC_2CTA_K=512"; do
-        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-e2e 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d.get('parity_class_argmax_agreement'), d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
+      for cfg in "DS_TC_2CTA=1" "DS_TC_2CTA=0"; do
+        env $cfg timeout 300 python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu-baseline 2>gpurun_out/${TAG}_bench_ab.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['ms_per_step'], d.get('parity_max_abs'), d.get('parity_class_argmax_agreement'), d['clocks'])" || tail -5 gpurun_out/${TAG}_bench_ab.err
       done 2>&1 | tee -a gpurun_out/${TAG}_probe_tc2.txt ;;
     py)
       timeout 900 python "$@" 2>&1 | tail -40 | tee gpurun_out/${TAG}_py.log ;;
