@@ -1480,7 +1480,7 @@ k_gemm_gnt(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUt
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
 static int gnt_two_cta();
-static constexpr int TC_2CTA_DEFAULT = 0;      // row-major kernel: CTA pair off / on by default (DS_TC_2CTA)
+static constexpr int TC_2CTA_DEFAULT = 1;      // row-major kernel: CTA pair off / on by default (DS_TC_2CTA)
 struct TcGemmPlan {
   CUtensorMap tm_a0, tm_a1, tm_w;
   TcEpi epi;
@@ -1622,12 +1622,17 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
     if (two_cta) gnt_cs = 2;                       // the pair is a cluster of 2
     if (gnt_cs != 2 || (g.N / BM) % 2 != 0) gnt_cs = 1;
   }
-  // row-major plain kernel, 128 x 256 tiles: DS_TC_2CTA = 0 off, 1 CTA pair for K >= DS_TC_2CTA_K (default 256)
+  // row-major plain kernel, 128 x 256 tiles: DS_TC_2CTA = 0 off, 1 (default) CTA pair where it measured faster --
+  // K >= DS_TC_2CTA_K (1024) or N >= DS_TC_2CTA_N (2048).  Same box, 4096 scenes (profiles/round2_probe_tc2.txt):
+  // 512 x 1024 51.0 -> 45.1 us, encoder K = 3072 128.3 -> 119.6 us, dec.l0 N = 3072 143.3 -> 137.1 us, but
+  // 512 x 512 31.2 -> 34.2 us and enc.l1 (N = 1024, K = 512) 51.4 -> 52.5 us; whole sample +1.4 % with the pair on
+  // every K >= 256 launch.  All 111 GPU tests ran green with the pair on every K >= 256 launch (a superset).
   int tc_two = 0;
   if (!gnt && !gn && p->bn == 256 && tc_uniform_issue()) {
     static const int m2 = getenv("DS_TC_2CTA") ? atoi(getenv("DS_TC_2CTA")) : TC_2CTA_DEFAULT;
-    static const int k2 = getenv("DS_TC_2CTA_K") ? atoi(getenv("DS_TC_2CTA_K")) : 256;
-    if (m2 && K >= k2) tc_two = 1;
+    static const int k2 = getenv("DS_TC_2CTA_K") ? atoi(getenv("DS_TC_2CTA_K")) : 1024;
+    static const int n2 = getenv("DS_TC_2CTA_N") ? atoi(getenv("DS_TC_2CTA_N")) : 2048;
+    if (m2 && (K >= k2 || g.N >= n2)) tc_two = 1;
   }
   const int gnt_un = g.n_obj == 21 ? GntCfg<21, true>::UN : (gnt_sc20 ? GntCfg<12, false, 20>::UN : GntCfg<12, true>::UN);
   const int gnt_tok = g.n_obj == 21 ? GntCfg<21, true>::TOK : (gnt_sc20 ? GntCfg<12, false, 20>::TOK : GntCfg<12, true>::TOK);
