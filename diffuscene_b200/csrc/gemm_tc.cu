@@ -12,7 +12,14 @@
 //               into a STAGES-deep shared-memory ring, completion on mbarriers
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block,
 //               accumulating into one of two TMEM buffers; tcgen05.commit releases smem slots / signals
-//               the epilogue
+//               the epilogue.  Both single-thread roles run their loops warp-uniformly and elect the issuing
+//               lane inside the PTX wrapper (tc_common.cuh): descriptors live in uniform registers and the
+//               four UTCHMMA of a k-block issue back to back.
+//   TWO = true  the CTA-pair instantiation (cluster of 2, tcgen05.mma.cta_group::2, M = 256): each CTA loads its
+//               own token tile and half of the weight tile, the even CTA issues for both, commits are multicast
+//               to both CTAs' barriers, both epilogues release the leader's TMEM-empty barrier.  Chosen by
+//               shape at plan creation (K >= 1024 or N >= 2048), a separate instantiation because a kernel
+//               that contains cta_group::2 instructions cannot be launched without a cluster.
 //   warps 2-9   epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns):
 //               tcgen05.ld (32 lanes x 32 columns) -> epilogue math -> bf16 -> HBM; double-buffered TMEM
 //               lets the epilogue of tile i overlap the MMAs of tile i+1.  Two epilogues:
