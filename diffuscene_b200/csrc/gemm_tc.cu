@@ -1635,7 +1635,7 @@ TcGemmPlan* tc_plan_create(const GemmArgs& g, int rows_capacity, char* err, int 
   // 512 x 512 31.2 -> 34.2 us and enc.l1 (N = 1024, K = 512) 51.4 -> 52.5 us; whole sample +1.4 % with the pair on
   // every K >= 256 launch.  All 111 GPU tests ran green with the pair on every K >= 256 launch (a superset).
   int tc_two = 0;
-  if (!gnt && !gn && p->bn == 256 && tc_uniform_issue()) {
+  if (!gnt && !gn && !g.no_pair && p->bn == 256 && tc_uniform_issue()) {
     static const int m2 = getenv("DS_TC_2CTA") ? atoi(getenv("DS_TC_2CTA")) : TC_2CTA_DEFAULT;
     static const int k2 = getenv("DS_TC_2CTA_K") ? atoi(getenv("DS_TC_2CTA_K")) : 1024;
     static const int n2 = getenv("DS_TC_2CTA_N") ? atoi(getenv("DS_TC_2CTA_N")) : 2048;

@@ -113,6 +113,10 @@ struct GemmArgs {
   const float* gamma;
   const float* beta;
   FilmRef film;
+  // tcgen05 backend: never use the CTA-pair instantiation for this GEMM.  Set by the training step: its GEMMs measured
+  // 4.5 % slower per iteration as pairs (26.8 k vs 28.0 k scenes/s, profiles/round2_final_bench_train_*), unlike the
+  // sampling path's large plain GEMMs
+  int no_pair;
 };
 template <typename T> void launch_gemm_simt(const GemmArgs& g, bool exact, cudaStream_t s);
 // fp32 A/W in, fp32 out (time / context FiLM tables; always fp32)
